@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec of 4096 parallel Stretch envs (BASELINE.json config 2:
+empty-floor scene, physics only) on N B200s, next to the CPU path timed on the host cores.
+
+One bench "step" = one control period of the rollout workload: a fresh uniform-random ctrl row
+per env (counter-based RNG keyed (seed, env, period, actuator)) held for 50
+mj_steps, i.e. 50 x nenv env-steps per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nenv 4096]
+
+`--impl reference` times the CPU restatement of the reference's mj_step path (oracle/, all host
+threads) on a bounded sample of the same workload -- the real mujoco==3.2.6 wheel cannot be
+installed in this image (no wheel in /opt/wheelhouse, no network; DESIGN.md "Reference arm").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden", "stretch_empty_floor.ssm")
+MJ_STEPS_PER_STEP = 50
+ALGO_BYTES_PER_ENV_STEP = 828  # 89 floats read + 118 floats written
+METRIC = "env-steps/sec (4096 parallel Stretch envs) at 1/2/4/8 B200 vs reference CPU"
+
+
+# ----------------------------------------------------------------------------- counter-based ctrl stream
+def _mix_np(x):
+    M = np.uint64(0xFFFFFFFF)
+    x = x & M
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def ctrl_np(seed, env0, nenv, period, lo, hi):
+    env = np.arange(env0, env0 + nenv, dtype=np.uint64)[:, None]
+    act = np.arange(len(lo), dtype=np.uint64)[None, :]
+    key = (np.uint64(seed) * np.uint64(0x9E3779B1) + env * np.uint64(0x85EBCA77) + np.uint64(period) * np.uint64(0xC2B2AE3D)
+           + act * np.uint64(0x27D4EB2F))
+    u = _mix_np(_mix_np(key)).astype(np.float64) / 4294967296.0
+    return (lo[None, :] + u * (hi - lo)[None, :])
+
+
+def ctrl_torch(seed, env0, nenv, period, lo, hi, device):
+    import torch
+    M = 0xFFFFFFFF
+
+    def mix(x):
+        x = x & M
+        x = x ^ (x >> 16); x = (x * 0x7FEB352D) & M
+        x = x ^ (x >> 15); x = (x * 0x846CA68B) & M
+        x = x ^ (x >> 16)
+        return x
+    env = torch.arange(env0, env0 + nenv, dtype=torch.int64, device=device)[:, None]
+    act = torch.arange(lo.numel(), dtype=torch.int64, device=device)[None, :]
+    key = (seed * 0x9E3779B1 + env * 0x85EBCA77 + period * 0xC2B2AE3D + act * 0x27D4EB2F) & 0xFFFFFFFFFFFF
+    u = mix(mix(key)).to(torch.float64) / 4294967296.0
+    return (lo[None, :] + u * (hi - lo)[None, :]).to(torch.float32)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) > 2 + k and r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_sample(nenv, nsteps_mj, periods, threads=0):
+    """Times the CPU path on `nenv` envs for `periods` control periods; returns env-steps/s."""
+    from oracle.oracle import OracleModel, lib
+    from stretch_mujoco_b200 import blob
+    raw = open(GOLDEN, "rb").read()
+    A, _ = blob.unpack(raw)
+    om = OracleModel(raw)
+    om.set_options(enable_lidar=False)
+    lo, hi = A["actuator_ctrlrange"][:, 0].copy(), A["actuator_ctrlrange"][:, 1].copy()
+    qpos = np.tile(A["qpos0"], (nenv, 1)); qvel = np.zeros((nenv, om.nv)); warm = np.zeros((nenv, om.nv)); t = np.zeros(nenv)
+    cores = threads or lib().om_max_threads()
+    times = []
+    for p in range(periods):
+        c = ctrl_np(0, 0, nenv, p, lo, hi)
+        t0 = time.perf_counter()
+        om.step(qpos, qvel, c, warm, t, nsteps=nsteps_mj, nthreads=cores)
+        times.append(time.perf_counter() - t0)
+    return nenv * nsteps_mj / np.array(times), cores, float(np.abs(qpos).sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    nenv = args.cpu_nenv
+    rates, cores, _ = cpu_sample(nenv, MJ_STEPS_PER_STEP, args.warmup + args.steps)
+    timed = rates[args.warmup:]
+    total_t = float((nenv * MJ_STEPS_PER_STEP / timed).sum())
+    value = nenv * MJ_STEPS_PER_STEP * len(timed) / total_t
+    sample = f"{nenv} envs x {MJ_STEPS_PER_STEP} mj_steps per step (bounded sample of the 4096-env workload)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(timed),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: 4096 parallel Stretch envs, empty-floor scene, physics only (no sensors)",
+                       "mj_steps_per_step": MJ_STEPS_PER_STEP, "nenv_timed": nenv},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the mujoco==3.2.6 mj_step path, not the MuJoCo binary"},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from stretch_mujoco_b200 import blob
+    from stretch_mujoco_b200.simulator import StretchMujocoSimulator
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: CUDA is required (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    raw = open(GOLDEN, "rb").read()
+    A, _ = blob.unpack(raw)
+    nenv = args.nenv                      # per GPU: envs shard with no data-path collective (weak scaling)
+    env0 = rank * nenv
+    sim = StretchMujocoSimulator(model_blob=raw, nenv=nenv, device=local)
+    sim.start(home=False)
+    B = sim.batch
+    lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev)
+    hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
+    lo_np, hi_np = A["actuator_ctrlrange"][:, 0].copy(), A["actuator_ctrlrange"][:, 1].copy()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    # ---- leg 1: device-resident inputs (ctrl drawn on the device before the timed region)
+    for p in range(W):
+        B.ctrl.copy_(ctrl_torch(0, env0, nenv, p, lo, hi, dev)); B.step(MJ_STEPS_PER_STEP)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = B.launches
+    with ClockSampler(local) as clocks:
+        barrier()
+        for k in range(K):
+            B.ctrl.copy_(ctrl_torch(0, env0, nenv, W + k, lo, hi, dev))
+            flush.fill_(k & 0xFF)           # L2 flush between timed iterations (outside the event pair)
+            ev[k][0].record()
+            B.step(MJ_STEPS_PER_STEP)
+            ev[k][1].record()
+        barrier()
+    launches = B.launches - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * nenv * MJ_STEPS_PER_STEP * K / (total_ms * 1e-3)
+    kernel_ms = float(np.mean(ms))
+
+    # ---- leg 2: end to end through the public API with host buffers (H2D ctrl, D2H status every step)
+    pin_ctrl = torch.empty(nenv, sim.dmodel.nu, dtype=torch.float32).pin_memory()
+    pin_status = torch.empty(nenv, 24, dtype=torch.float32).pin_memory()
+    sim.batch.reset()
+    for p in range(W):
+        pin_ctrl.copy_(torch.from_numpy(ctrl_np(0, env0, nenv, p, lo_np, hi_np).astype(np.float32)))
+        sim.set_ctrl(pin_ctrl); sim.step(MJ_STEPS_PER_STEP); pin_status.copy_(sim.pull_status().raw, non_blocking=True)
+    host_ctrl = [torch.from_numpy(ctrl_np(0, env0, nenv, W + k, lo_np, hi_np).astype(np.float32)) for k in range(K)]
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_ms = 0.0
+    for k in range(K):
+        pin_ctrl.copy_(host_ctrl[k])
+        flush.fill_(k & 0xFF)
+        e0.record()
+        sim.set_ctrl(pin_ctrl)                                    # H2D from pinned host memory
+        sim.step(MJ_STEPS_PER_STEP)                               # command kernel + physics kernel
+        pin_status.copy_(sim.pull_status().raw, non_blocking=True)  # status kernel + D2H
+        e1.record()
+        e1.synchronize()
+        e2e_ms += e0.elapsed_time(e1)
+    barrier()
+    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * nenv * MJ_STEPS_PER_STEP * K / (float(e2e_t.item()) * 1e-3)
+
+    # ---- end-of-rollout metrics: the path's only collective
+    metrics = torch.stack([torch.tensor(float(nenv * MJ_STEPS_PER_STEP * K), device=dev), torch.tensor(total_ms, device=dev, dtype=torch.float32),
+                           B.qpos.abs().sum(), B.ncon.sum().float(), (B.env_flags & 1).sum().float()]).float()
+    if world > 1:
+        gathered = torch.empty(world, metrics.numel(), device=dev)
+        dist.all_gather_into_tensor(gathered, metrics)
+    else:
+        gathered = metrics[None]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALGO_BYTES_PER_ENV_STEP * nenv * MJ_STEPS_PER_STEP / (kernel_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 4096 parallel Stretch envs per GPU, empty-floor scene, physics only (no sensors)",
+                       "nenv_per_gpu": nenv, "mj_steps_per_step": MJ_STEPS_PER_STEP, "solver": "Newton (reference default)",
+                       "ctrl": "uniform over ctrlrange, counter-based RNG (seed 0, env, period, actuator), redrawn every step",
+                       "l2": "flushed between timed iterations (256 MiB fill outside the timed event pair)",
+                       "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": nenv * sim.dmodel.nu * 4,
+                    "d2h_bytes_per_step": nenv * 24 * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "ss_physics_kernel", "kernel_ms": kernel_ms,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "note": "physics is issue/latency bound, not HBM bound: 828 algorithmic B per env-step "
+                                 "(SURVEY.md 8(d)); see profiles/ for issue-slot utilisation"},
+            "rollout_metrics": {"env_steps": float(gathered[:, 0].sum()), "sum_abs_qpos": float(gathered[:, 2].sum()),
+                                "contacts_last_step": float(gathered[:, 3].sum()), "envs_reset": float(gathered[:, 4].sum())}}
+    if world == 1 and not args.no_cpu:
+        rates, cores, _ = cpu_sample(args.cpu_nenv, MJ_STEPS_PER_STEP, 4)
+        line["cpu_baseline"] = {"value": float(np.median(rates[1:])), "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_nenv} envs x {MJ_STEPS_PER_STEP} mj_steps x 3 periods of the same ctrl stream",
+                                "note": "CPU restatement of the mujoco==3.2.6 mj_step path (oracle/), not the MuJoCo binary"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nenv", type=int, default=4096)
+    ap.add_argument("--cpu-nenv", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

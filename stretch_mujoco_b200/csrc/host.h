@@ -1,0 +1,37 @@
+// Host-side handle definitions shared by the translation units of libstretchsim.
+#pragma once
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "../../include/ss_blob.h"
+#include "../../include/stretchsim.h"
+#include "model.cuh"
+#include "rays.cuh"
+
+struct ss_model {
+  std::vector<unsigned char> blob;  // host copy of the compiled model (names, fp64 masters)
+  ss_blob b;
+  ss_dims dims;
+  int device;
+  int nrange;
+  DevModel dm;
+  RayModel rm;
+  std::vector<float> qpos0_host;
+  std::vector<void*> dev_allocs;
+};
+
+struct ss_batch {
+  const ss_model* model;
+  int nenv;
+  ss_buffers bufs;
+  ss_debug_buffers dbg;
+  DevModel dm;  // model + this batch's buffer sizes and shared-memory layout
+  size_t smem_per_env;
+  int warps_per_block, grid;
+  long launches;
+};
+
+int ss_fail(const char* fmt, ...);
+int ss_rays_model_init(ss_model* M);
+int ss_rays_set_fovy(ss_model* M, const double* fovy, size_t bytes);

@@ -1,0 +1,24 @@
+// Device-side ray-geometry description (lidar + camera kernels).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct RayModel {
+  int present;
+  int nraygeom, nmesh, ngeom, nbody, ncam, nsite, nlight, nsky, headlight_active;
+  float extent, znear, zfar;
+  const int *rg_geom, *rg_type, *rg_body, *rg_mesh, *rg_group;   // ray-visible geoms (alpha>0, deduplicated)
+  const float *rg_pos, *rg_quat, *rg_size, *rg_rbound, *rg_shade; // shade: rgb, specular, shininess, emission (6)
+  const int *rmesh_vertadr, *rmesh_faceadr, *rmesh_facenum, *rmesh_bvhadr;
+  const float4* tri;        // 3 float4 per triangle: v0, e1, e2 (mesh frame), BVH leaf order
+  const float4* bvh;        // 2 float4 per node: (min.xyz, left|~firstTri), (max.xyz, right|count)
+  const int *cam_bodyid, *site_bodyid;
+  const float *cam_pos, *cam_quat, *cam_fovy, *site_pos, *site_quat;
+  const int *range_site;    // site id per rangefinder sensor
+  const int *range_adr;     // sensordata address per rangefinder
+  const float* range_cutoff;
+  int nrange;
+  float headlight[9], sky[6];
+  const int *light_bodyid, *light_directional;
+  const float *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;
+};

@@ -1,0 +1,121 @@
+"""Scene loader / model compiler checks.  CPU only.
+Tests that read the reference's MJCF files skip when /root/reference is not mounted."""
+import numpy as np
+import pytest
+
+from conftest import have_reference
+from stretch_mujoco_b200 import blob, compiler
+from stretch_mujoco_b200.mjcf import quat2mat
+
+needs_ref = pytest.mark.skipif(not have_reference(), reason="reference MJCF files not available")
+
+
+@pytest.fixture(scope="module")
+def model_E():
+    from stretch_mujoco_b200 import scenes
+    return scenes.compile_empty_floor(with_render=False)
+
+
+def test_blob_roundtrip(arrays_E, blob_empty_floor):
+    A, names = arrays_E
+    again = blob.pack(A, names)
+    B, names2 = blob.unpack(again)
+    assert names == names2 and A.keys() == B.keys()
+    for k in A:
+        assert np.array_equal(A[k], B[k]), k
+
+
+def test_golden_sizes(arrays_E):
+    A, _ = arrays_E
+    nq, nv, nu, nbody, njnt, ngeom, nsite, ncam, nten, neq, nsens, nsd, nkey, nM, npair, nmesh = A["sizes"]
+    # nq 27, nv 26, nu 10, nbody 38, njnt 21, nM 260; 360 lidar sites + IMU; 848+51 pairs
+    assert (nq, nv, nu, nbody, njnt, nM) == (27, 26, 10, 38, 21, 260)
+    assert (nsite, nsens, nsd, ncam, neq, nkey) == (361, 362, 366, 5, 5, 2)
+    assert npair == 899 and ngeom == 128
+
+
+def test_default_scene_sizes(blob_default_scene):
+    A, _ = blob.unpack(blob_default_scene)
+    assert tuple(A["sizes"][:6]) == (48, 44, 10, 43, 24, 154)  # SURVEY.md A.1 default scene.xml
+
+
+@needs_ref
+def test_golden_matches_fresh_compile(model_E, arrays_E):
+    A, _ = arrays_E
+    for k, v in model_E.arrays.items():
+        assert k in A, k
+        assert np.allclose(A[k], v, rtol=0, atol=1e-12), k
+
+
+@needs_ref
+def test_masses(model_E):
+    m = model_E
+    bid = lambda n: m.name2id(compiler.OBJ_BODY, n)
+    exp = {"base_link": 25.0, "link_mast": 1.8285, "link_head": 0.833027236718691, "laser": 0.24, "link_lift": 3.0,
+           "link_right_wheel": 0.15, "link_arm_l4": 0.168095, "link_arm_l0": 0.28501, "link_wrist_yaw": 0.1445,
+           "link_SG3_gripper_body": 0.29, "link_d405": 0.29 + 2 * 3.6e-6, "link_gripper_slider": 0.05,
+           "link_gripper_finger_left": 0.10, "link_gripper_finger_right": 0.15, "rubber_tip_left": 0.005,
+           "link_head_tilt": 0.262217, "link_SE3_head_nav_cam": 0.028346169831483}
+    for n, mass in exp.items():
+        assert m.body_mass[bid(n)] == pytest.approx(mass, rel=1e-9), n
+    assert m.body_mass.sum() == pytest.approx(33.695, abs=1e-3)
+
+
+@needs_ref
+def test_actuators_and_limits(model_E):
+    m = model_E
+    names = m.names[compiler.OBJ_ACTUATOR]
+    assert names == ["left_wheel_vel", "right_wheel_vel", "lift", "arm", "wrist_yaw", "wrist_pitch", "wrist_roll",
+                     "gripper", "head_pan", "head_tilt"]
+    a = names.index
+    # velocity servo kv 20 with gear 3; position servos inherit the class-level general/position parameters
+    assert m.actuator_gainprm[a("left_wheel_vel"), 0] == 20 and m.actuator_biasprm[a("left_wheel_vel"), 2] == -20
+    assert m.actuator_gear[a("left_wheel_vel")] == 3
+    assert tuple(m.actuator_biasprm[a("lift")]) == (0, -400, -100) and tuple(m.actuator_forcerange[a("lift")]) == (-70, 70)
+    assert tuple(m.actuator_biasprm[a("arm")]) == (0, -150, -10) and m.actuator_trntype[a("arm")] == 1
+    assert tuple(m.actuator_biasprm[a("gripper")]) == (0, -4000, -124)
+    assert tuple(m.actuator_biasprm[a("head_tilt")]) == (0, -10, 0)
+    # compiled joint limits quoted in enums/actuators.py:69-89
+    j = m.names[compiler.OBJ_JOINT].index
+    rng = lambda n: tuple(m.jnt_range[j(n)])
+    assert rng("joint_lift") == (0.0, 1.1) and rng("joint_arm_l0") == (0.0, 0.13)
+    assert rng("joint_wrist_yaw") == (-1.39, 4.42) and rng("joint_wrist_pitch") == (-1.57, 0.56)
+    assert rng("joint_head_pan") == (-4.04, 1.73) and rng("joint_head_tilt") == (-1.53, 0.79)
+    assert rng("joint_gripper_slide") == (-0.02, 0.04) and m.jnt_limited[j("joint_left_wheel")] == 0
+    assert m.key_ctrl[0].tolist() == [0, 0, 0.6, 0.1, 0, 0, 0, 0, 0, 0]
+
+
+@needs_ref
+def test_frames_at_qpos0(model_E):
+    """Frame-convention KATs of SURVEY.md Appendix A.2 (camera / lidar / IMU placement)."""
+    m = model_E
+    xpos, xquat, _, _ = compiler.fk_numpy(m, m.qpos0)
+    cam = m.names[compiler.OBJ_CAMERA].index
+
+    def cam_frame(n):
+        c = cam(n); b = m.cam_bodyid[c]
+        R = quat2mat(xquat[b]) @ quat2mat(m.cam_quat[c])
+        return xpos[b] + quat2mat(xquat[b]) @ m.cam_pos[c], R
+
+    p, R = cam_frame("d435i_camera_rgb")
+    assert np.allclose(p, [0.045, -0.003, 1.322], atol=2e-3)
+    assert np.allclose(-R[:, 2], [1, 0, 0], atol=2e-2) and np.allclose(R[:, 1], [0, -1, 0], atol=2e-2)
+    p, R = cam_frame("d405_rgb")
+    assert np.allclose(p, [-0.021, -0.245, 0.176], atol=2e-3)
+    assert np.allclose(-R[:, 2], [0.002, -0.984, -0.176], atol=5e-3)
+    sid = m.names[compiler.OBJ_SITE].index
+    for name, d in (("lidar000", [-1, 0, 0]), ("lidar090", [0, -1, 0]), ("lidar180", [1, 0, 0])):
+        s = sid(name); b = m.site_bodyid[s]
+        z = (quat2mat(xquat[b]) @ quat2mat(m.site_quat[s]))[:, 2]
+        assert np.allclose(z, d, atol=2e-3), name
+    s = sid("base_imu"); b = m.site_bodyid[s]
+    R = quat2mat(xquat[b]) @ quat2mat(m.site_quat[s])
+    assert np.allclose(R[:, 0], [0, -1, 0], atol=1e-3) and np.allclose(R[:, 2], [0, 0, -1], atol=1e-3)
+
+
+@needs_ref
+def test_lidar_sensor_names(model_E):
+    names = model_E.names[compiler.OBJ_SENSOR]
+    # enums/stretch_sensors.py:33-41 expects base_lidar000 .. base_lidar359
+    assert names[0] == "base_gyro" and names[1] == "base_accel"
+    assert names[2:] == [f"base_lidar{i:03d}" for i in range(360)]

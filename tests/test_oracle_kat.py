@@ -1,0 +1,117 @@
+"""Pins the CPU oracle.  CPU only.
+
+The reference's tests hold no golden vectors; the anchors that exist are numbers the reference
+itself PRINTED after running its own MuJoCo path: `docs/getting_started.ipynb:729-751` (status at
+t = 8.26 s after `home`), `:799` (head-tilt limit saturation), `README.md:136-145`.  The oracle
+reproduces them to 4-8 digits, which pins the loader's mass properties, gravcomp, the actuator
+model, friction loss, joint limits, equality constraints and the Newton solve end to end.
+"""
+import numpy as np
+import pytest
+
+from stretch_mujoco_b200 import compiler
+
+
+def _rollout(om, A, nsteps, ctrl=None, want=("act_length", "act_velocity")):
+    qpos = A["qpos0"][None].copy(); qvel = np.zeros((1, om.nv)); warm = np.zeros((1, om.nv)); t = np.zeros(1)
+    ctrl = A["key_ctrl"][0][None].copy() if ctrl is None else ctrl
+    out = om.step(qpos, qvel, ctrl, warm, t, nsteps=nsteps, want=want)
+    return qpos, qvel, warm, t, out
+
+
+def test_home_status_matches_reference_notebook(oracle_E, arrays_E):
+    A, _ = arrays_E
+    qpos, qvel, warm, t, o = _rollout(oracle_E, A, 4130)  # t = 8.26 s
+    L, V = o["act_length"][0], o["act_velocity"][0]
+    ref = dict(lift=(0.5905520090306994, 2.2063552289719744e-4), arm=(0.09999622635034094, 1.34e-10),
+               head_pan=(-5.005046374741913e-06, 0), head_tilt=(-0.004519272499335126, 0),
+               wrist_yaw=(9.232975816659571e-05, -3.3150607193177336e-05), wrist_pitch=(-0.005324523093874352, 0),
+               wrist_roll=(-9.586627571896982e-05, 0))
+    idx = dict(lift=2, arm=3, wrist_yaw=4, wrist_pitch=5, wrist_roll=6, head_pan=8, head_tilt=9)
+    assert t[0] == pytest.approx(8.26, abs=1e-9)
+    assert L[idx["lift"]] == pytest.approx(ref["lift"][0], abs=2e-5)       # mid-creep value, 5 digits
+    assert V[idx["lift"]] == pytest.approx(ref["lift"][1], rel=2e-2)
+    assert L[idx["arm"]] == pytest.approx(ref["arm"][0], abs=1e-8)
+    assert L[idx["head_tilt"]] == pytest.approx(ref["head_tilt"][0], abs=1e-8)
+    assert L[idx["head_pan"]] == pytest.approx(ref["head_pan"][0], abs=1e-8)
+    assert L[idx["wrist_pitch"]] == pytest.approx(ref["wrist_pitch"][0], abs=1e-8)
+    assert L[idx["wrist_roll"]] == pytest.approx(ref["wrist_roll"][0], abs=1e-8)
+    assert L[idx["wrist_yaw"]] == pytest.approx(ref["wrist_yaw"][0], abs=2e-5)
+    # gripper: sim 0 maps to -0.0639975 in the real range (config.py:4-5, mujoco_server.py:517-525)
+    g = (L[7] + 0.02) * (0.56 + 0.376) / 0.06 - 0.376
+    assert g == pytest.approx(-0.06399746756801022, abs=1e-5)
+
+
+def test_head_tilt_limit_saturation(oracle_E, arrays_E):
+    A, _ = arrays_E
+    om = oracle_E
+    qpos, qvel, warm, t, _ = _rollout(om, A, 2000)
+    ctrl = A["key_ctrl"][0][None].copy(); ctrl[0, 9] = -2.0  # move_to('head_tilt', -2.0)
+    o = om.step(qpos, qvel, ctrl, warm, t, nsteps=3000, want=("act_length",))
+    assert o["act_length"][0, 9] == pytest.approx(-1.52257, abs=2e-5)  # docs/getting_started.ipynb:799
+
+
+def test_mass_matrix_matches_independent_jacobian_form(oracle_E, blob_empty_floor):
+    from stretch_mujoco_b200 import blob
+    m = blob.load.__globals__["unpack"](blob_empty_floor)
+    model = compiler.Model(); model.arrays, model.names = m
+    rng = np.random.default_rng(1)
+    q = model.qpos0.copy()
+    q[7:] += rng.uniform(-0.1, 0.1, size=len(q) - 7)
+    quat = rng.normal(size=4); q[3:7] = quat / np.linalg.norm(quat)
+    M2 = compiler.mass_matrix_numpy(model, q)[0]
+    o = oracle_E.forward(q[None], np.zeros((1, oracle_E.nv)), np.zeros((1, oracle_E.nu)), want=("M",))
+    assert np.allclose(o["M"][0], M2, rtol=0, atol=1e-10 * np.abs(M2).max())
+    assert np.all(np.linalg.eigvalsh(M2) > 0)
+
+
+def test_wheel_and_caster_contacts_at_rest(oracle_E, arrays_E, settled_home_E):
+    A, names = arrays_E
+    qpos, qvel, warm, ctrl = settled_home_E
+    o = oracle_E.forward(qpos[None], qvel[None], ctrl[None], warm[None], want=("ncon", "contact_geom", "nefc", "contact_dist"))
+    gname = names[compiler.OBJ_GEOM]
+    assert o["ncon"][0] == 5  # caster sphere + 2 per wheel cylinder (plane-cylinder rim points)
+    types = sorted(int(A["geom_type"][g]) for g in o["contact_geom"][0, :5, 1])
+    assert types == [2, 5, 5, 5, 5] and all(gname[g] == "floor" for g in o["contact_geom"][0, :5, 0])
+    assert o["nefc"][0] == 5 + 12 + 0 + 1 + 4 * 6  # equality + friction loss + limits + caster + condim-6 wheels
+    assert np.all(o["contact_dist"][0, :5] < 0) and np.all(o["contact_dist"][0, :5] > -2e-3)
+
+
+def test_free_fall_and_accelerometer(blob_default_scene):
+    """object1 of scene.xml is a free box dropped from z=0.6: analytic free fall until it lands."""
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    A, names = blob.unpack(blob_default_scene)
+    om = OracleModel(blob_default_scene)
+    qpos = A["qpos0"][None].copy(); qvel = np.zeros((1, om.nv)); warm = np.zeros((1, om.nv)); t = np.zeros(1)
+    ctrl = A["key_ctrl"][0][None].copy()
+    z0 = qpos[0, 34 + 2]
+    n = 50
+    om.step(qpos, qvel, ctrl, warm, t, nsteps=n)
+    h = 0.002
+    # semi-implicit Euler: v_k = -g h k ; z_n = z0 - g h^2 n(n+1)/2
+    assert qvel[0, 32 + 2] == pytest.approx(-9.81 * h * n, rel=1e-9)
+    assert qpos[0, 34 + 2] == pytest.approx(z0 - 9.81 * h * h * n * (n + 1) / 2, abs=1e-12)
+
+
+def test_imu_at_rest(oracle_E, settled_home_E):
+    qpos, qvel, warm, ctrl = settled_home_E
+    o = oracle_E.forward(qpos[None], qvel[None], ctrl[None], warm[None], want=("sensordata",))
+    gyro, acc = o["sensordata"][0, :3], o["sensordata"][0, 3:6]
+    assert np.abs(gyro).max() < 1e-2
+    # IMU is mounted upside-down: reads ~(0, 0, -9.81) at rest
+    assert acc[2] == pytest.approx(-9.81, abs=0.1) and np.abs(acc[:2]).max() < 0.2
+
+
+def test_solver_optimality(oracle_E, settled_home_E):
+    """At the solution M*qacc = qfrc_smooth + J^T f (stationarity of the Newton objective)."""
+    qpos, qvel, warm, ctrl = settled_home_E
+    rng = np.random.default_rng(3)
+    qv = qvel + rng.normal(scale=0.05, size=qvel.shape)
+    o = oracle_E.forward(qpos[None], qv[None], ctrl[None], None, maxefc=96,
+                         want=("M", "qacc", "qfrc_constraint", "qacc_smooth", "efc_J", "efc_force", "nefc"))
+    M, qacc = o["M"][0], o["qacc"][0]
+    lhs = M @ (qacc - o["qacc_smooth"][0])
+    assert np.allclose(lhs, o["qfrc_constraint"][0], atol=1e-6 * max(1.0, np.abs(lhs).max()))
+    n = o["nefc"][0]
+    assert np.allclose(o["efc_J"][0, :n].T @ o["efc_force"][0, :n], o["qfrc_constraint"][0], atol=1e-9)
