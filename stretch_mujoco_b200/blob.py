@@ -15,6 +15,7 @@ is the hook SURVEY.md §7.1 asks for should a MuJoCo install ever become reachab
 from __future__ import annotations
 
 import struct
+import zlib
 
 import numpy as np
 
@@ -74,14 +75,21 @@ def unpack(buf: bytes):
 
 
 def save(path: str, model) -> None:
+    """`.ssm` = raw blob; `.ssm.z` = zlib-compressed blob (used for the fixtures that carry meshes)."""
+    raw = pack(model.arrays, model.names)
     with open(path, "wb") as fh:
-        fh.write(pack(model.arrays, model.names))
+        fh.write(zlib.compress(raw, 9) if path.endswith(".z") else raw)
+
+
+def read_bytes(path: str) -> bytes:
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    return zlib.decompress(raw) if path.endswith(".z") else raw
 
 
 def load(path: str):
     from .compiler import Model
-    with open(path, "rb") as fh:
-        arrays, names = unpack(fh.read())
+    arrays, names = unpack(read_bytes(path))
     m = Model()
     m.arrays, m.names = arrays, names
     return m

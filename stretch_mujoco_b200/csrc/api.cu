@@ -313,7 +313,11 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   return 0;
 }
 
-extern "C" void ss_batch_free(ss_batch* B) { delete B; }
+extern "C" void ss_batch_free(ss_batch* B) {
+  if (!B) return;
+  if (B->ray_xf) { cudaSetDevice(B->model->device); cudaFree(B->ray_xf); }
+  delete B;
+}
 extern "C" long ss_batch_launch_count(const ss_batch* B) { return B ? B->launches : 0; }
 
 extern "C" int ss_batch_set_debug(ss_batch* B, const ss_debug_buffers* d) {

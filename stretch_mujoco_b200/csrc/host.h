@@ -17,7 +17,7 @@ struct ss_model {
   int nrange;
   DevModel dm;
   RayModel rm;
-  std::vector<float> qpos0_host;
+  std::vector<float> qpos0_host, cam_fovy_host;
   std::vector<void*> dev_allocs;
 };
 
@@ -30,6 +30,7 @@ struct ss_batch {
   size_t smem_per_env;
   int warps_per_block, grid;
   long launches;
+  float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
 };
 
 int ss_fail(const char* fmt, ...);

@@ -1,8 +1,615 @@
-// Ray casting kernels of libstretchsim: lidar (S2/L1) and pinhole camera (C1-C4).
+// Ray casting kernels of libstretchsim: 2-D spinning lidar (rows S2/L1) and pinhole RGB+depth
+// camera (rows C1-C4 of SURVEY.md §8(a)).
+//
+// Replaces the <rangefinder> evaluation inside mj_step that the reference reads out at
+// stretch_mujoco/mujoco_server_sensor_manager.py:77-83 and mujoco.Renderer.update_scene()+render()
+// at stretch_mujoco/mujoco_server_camera_manager.py:135-137.
+//
+// Data layout: triangle soups live once in HBM/L2 in mesh-local coordinates (shared by all envs)
+// behind one BVH per mesh; per env only the 12-float world transform of each ray-visible geom is
+// produced (ray_prepare_kernel) and staged in shared memory by the tracing blocks.  The camera
+// kernel culls geoms against each 16x16 pixel tile's frustum before tracing and writes RGB/depth
+// rows contiguously (the HBM-bound part: W*H*7 algorithmic bytes per env-frame).
 #include "host.h"
-int ss_rays_model_init(ss_model* M) { M->rm.present = 0; return 0; }
-int ss_rays_set_fovy(ss_model* M, const double* fovy, size_t bytes) { return ss_fail("ray geometry not built"); }
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#define CUDA_OK(x)                                                                      \
+  do {                                                                                  \
+    cudaError_t e_ = (x);                                                               \
+    if (e_ != cudaSuccess) return ss_fail("%s: %s", #x, cudaGetErrorString(e_));        \
+  } while (0)
+
+// ----------------------------------------------------------------------------- host: BVH build
+namespace {
+struct HostBVH {
+  std::vector<float4> nodes;  // 2 per node
+  std::vector<float4> tris;   // 3 per triangle (v0, e1, e2), leaf order
+};
+
+struct Builder {
+  const float* V; const int* F; std::vector<int> order; std::vector<float> cen; HostBVH* out; int tri_base;
+  void bounds(int t, float* lo, float* hi) const {
+    const int* f = F + 3 * t;
+    for (int k = 0; k < 3; k++) {
+      float a = V[3 * f[0] + k], b = V[3 * f[1] + k], c = V[3 * f[2] + k];
+      lo[k] = std::min(a, std::min(b, c)); hi[k] = std::max(a, std::max(b, c));
+    }
+  }
+  int build(int first, int count) {
+    int id = (int)out->nodes.size() / 2;
+    out->nodes.push_back(make_float4(0, 0, 0, 0)); out->nodes.push_back(make_float4(0, 0, 0, 0));
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = first; i < first + count; i++) {
+      float a[3], b[3];
+      bounds(order[i], a, b);
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], a[k]); hi[k] = std::max(hi[k], b[k]);
+        clo[k] = std::min(clo[k], cen[3 * order[i] + k]); chi[k] = std::max(chi[k], cen[3 * order[i] + k]);
+      }
+    }
+    int ax = 0;
+    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+    int left, right;
+    if (count <= 4 || !(chi[ax] > clo[ax])) {
+      left = ~(tri_base + first); right = count;  // leaf: first triangle (global index, complemented), count
+    } else {
+      int mid = first + count / 2;
+      std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                       [&](int a, int b) { return cen[3 * a + ax] < cen[3 * b + ax]; });
+      left = build(first, mid - first);
+      right = build(mid, first + count - mid);
+    }
+    out->nodes[2 * id] = make_float4(lo[0], lo[1], lo[2], __int_as_float_host(left));
+    out->nodes[2 * id + 1] = make_float4(hi[0], hi[1], hi[2], __int_as_float_host(right));
+    return id;
+  }
+  static float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
+};
+}  // namespace
+
+template <typename T>
+static const T* upload(ss_model* M, const std::vector<T>& v) {
+  void* p = nullptr;
+  size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+  if (cudaMalloc(&p, n) != cudaSuccess) return nullptr;
+  if (!v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  M->dev_allocs.push_back(p);
+  return (const T*)p;
+}
+static std::vector<float> f32(const ss_blob& b, const char* name) {
+  const double* p = ss_blob_f64(&b, name);
+  size_t n = ss_blob_count(&b, name);
+  std::vector<float> v(n);
+  for (size_t i = 0; i < n; i++) v[i] = (float)p[i];
+  return v;
+}
+static std::vector<int> i32(const ss_blob& b, const char* name) {
+  const int32_t* p = ss_blob_i32(&b, name);
+  size_t n = ss_blob_count(&b, name);
+  return std::vector<int>(p, p + n);
+}
+
+int ss_rays_model_init(ss_model* M) {
+  RayModel& r = M->rm;
+  memset(&r, 0, sizeof(r));
+  const ss_blob& b = M->b;
+  if (!ss_blob_find(&b, "raygeom_id")) return 0;  // physics-only blob
+  std::vector<int> rg = i32(b, "raygeom_id"), gtype = i32(b, "geom_type"), gbody = i32(b, "geom_bodyid"),
+                   gdata = i32(b, "geom_dataid"), ggroup = i32(b, "geom_group");
+  std::vector<float> gpos = f32(b, "geom_pos"), gquat = f32(b, "geom_quat"), gsize = f32(b, "geom_size"),
+                     grb = f32(b, "geom_rbound"), gshade = f32(b, "geom_shade");
+  std::vector<int> t_type, t_body, t_mesh, t_group;
+  std::vector<float> t_pos, t_quat, t_size, t_rb, t_shade;
+  for (int g : rg) {
+    t_type.push_back(gtype[g]); t_body.push_back(gbody[g]); t_mesh.push_back(gdata[g]); t_group.push_back(ggroup[g]);
+    for (int k = 0; k < 3; k++) { t_pos.push_back(gpos[3 * g + k]); t_size.push_back(gsize[3 * g + k]); }
+    for (int k = 0; k < 4; k++) t_quat.push_back(gquat[4 * g + k]);
+    for (int k = 0; k < 8; k++) t_shade.push_back(gshade[8 * g + k]);
+    t_rb.push_back(grb[g]);
+  }
+  // per-mesh BVH over the triangle soup
+  std::vector<int> vadr = i32(b, "rmesh_vertadr"), fadr = i32(b, "rmesh_faceadr"), fnum = i32(b, "rmesh_facenum");
+  const float* V = ss_blob_f32(&b, "rmesh_vert");
+  const int32_t* F = ss_blob_i32(&b, "rmesh_face");
+  HostBVH H;
+  std::vector<int> bvhadr(vadr.size(), -1);
+  for (size_t mid = 0; mid < vadr.size(); mid++) {
+    if (fadr[mid] < 0 || fnum[mid] <= 0) continue;
+    Builder B;
+    B.V = V + 3 * (size_t)vadr[mid]; B.F = F + 3 * (size_t)fadr[mid]; B.out = &H; B.tri_base = (int)H.tris.size() / 3;
+    int nf = fnum[mid];
+    B.order.resize(nf); std::iota(B.order.begin(), B.order.end(), 0);
+    B.cen.resize(3 * (size_t)nf);
+    for (int t = 0; t < nf; t++)
+      for (int k = 0; k < 3; k++) B.cen[3 * t + k] = (B.V[3 * B.F[3 * t] + k] + B.V[3 * B.F[3 * t + 1] + k] + B.V[3 * B.F[3 * t + 2] + k]) / 3.0f;
+    bvhadr[mid] = B.build(0, nf);
+    for (int i = 0; i < nf; i++) {
+      const int* f = B.F + 3 * B.order[i];
+      const float *a = B.V + 3 * f[0], *c1 = B.V + 3 * f[1], *c2 = B.V + 3 * f[2];
+      H.tris.push_back(make_float4(a[0], a[1], a[2], 0));
+      H.tris.push_back(make_float4(c1[0] - a[0], c1[1] - a[1], c1[2] - a[2], 0));
+      H.tris.push_back(make_float4(c2[0] - a[0], c2[1] - a[1], c2[2] - a[2], 0));
+    }
+  }
+  r.present = 1;
+  r.nraygeom = (int)rg.size(); r.nmesh = (int)vadr.size(); r.ngeom = M->dims.ngeom; r.nbody = M->dims.nbody;
+  r.ncam = M->dims.ncam; r.nsite = M->dims.nsite;
+  r.extent = (float)ss_blob_f64(&b, "stat_extent")[0];
+  r.znear = (float)ss_blob_f64(&b, "vis_map")[0]; r.zfar = (float)ss_blob_f64(&b, "vis_map")[1];
+  r.rg_geom = upload(M, rg); r.rg_type = upload(M, t_type); r.rg_body = upload(M, t_body); r.rg_mesh = upload(M, t_mesh);
+  r.rg_group = upload(M, t_group); r.rg_pos = upload(M, t_pos); r.rg_quat = upload(M, t_quat); r.rg_size = upload(M, t_size);
+  r.rg_rbound = upload(M, t_rb); r.rg_shade = upload(M, t_shade);
+  r.rmesh_bvhadr = upload(M, bvhadr);
+  r.tri = upload(M, H.tris); r.bvh = upload(M, H.nodes);
+  r.cam_bodyid = upload(M, i32(b, "cam_bodyid")); r.cam_pos = upload(M, f32(b, "cam_pos")); r.cam_quat = upload(M, f32(b, "cam_quat"));
+  M->cam_fovy_host = f32(b, "cam_fovy");
+  r.cam_fovy = upload(M, M->cam_fovy_host);
+  r.site_bodyid = upload(M, i32(b, "site_bodyid")); r.site_pos = upload(M, f32(b, "site_pos")); r.site_quat = upload(M, f32(b, "site_quat"));
+  std::vector<int> stype = i32(b, "sensor_type"), sobj = i32(b, "sensor_objid"), sadr = i32(b, "sensor_adr"), rs, ra;
+  std::vector<float> scut = f32(b, "sensor_cutoff"), rc;
+  for (size_t s = 0; s < stype.size(); s++)
+    if (stype[s] == SENS_RANGE) { rs.push_back(sobj[s]); ra.push_back(sadr[s]); rc.push_back(scut[s]); }
+  r.nrange = (int)rs.size();
+  r.range_site = upload(M, rs); r.range_adr = upload(M, ra); r.range_cutoff = upload(M, rc);
+  std::vector<float> hl = f32(b, "vis_headlight"), sky = f32(b, "skybox_rgb");
+  for (int k = 0; k < 9; k++) r.headlight[k] = hl[k];
+  r.nsky = (int)sky.size() / 3;
+  for (int k = 0; k < 6; k++) r.sky[k] = k < (int)sky.size() ? sky[k] : 0.f;
+  r.headlight_active = ss_blob_i32(&b, "vis_headlight_active")[0];
+  r.nlight = (int)ss_blob_count(&b, "light_bodyid");
+  r.light_bodyid = upload(M, i32(b, "light_bodyid")); r.light_directional = upload(M, i32(b, "light_directional"));
+  r.light_pos = upload(M, f32(b, "light_pos")); r.light_dir = upload(M, f32(b, "light_dir"));
+  r.light_ambient = upload(M, f32(b, "light_ambient")); r.light_diffuse = upload(M, f32(b, "light_diffuse"));
+  r.light_specular = upload(M, f32(b, "light_specular"));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ss_fail("ray geometry upload failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ss_rays_set_fovy(ss_model* M, const double* fovy, size_t bytes) {
+  if (!M->rm.present) return ss_fail("model has no ray geometry");
+  if (bytes != M->cam_fovy_host.size() * sizeof(double)) return ss_fail("cam_fovy: expected %zu doubles", M->cam_fovy_host.size());
+  for (size_t i = 0; i < M->cam_fovy_host.size(); i++) M->cam_fovy_host[i] = (float)fovy[i];
+  CUDA_OK(cudaMemcpy((void*)M->rm.cam_fovy, M->cam_fovy_host.data(), M->cam_fovy_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int ss_model_num_rangefinders(const ss_model* M) { return M ? M->nrange : 0; }
-extern "C" int ss_batch_lidar(ss_batch* B, float* out_dev, ss_stream s) { return ss_fail("ray geometry not built"); }
-extern "C" int ss_batch_rays(ss_batch* B, int nray, const float* o, const float* d, int gm, int be, float* dist, int32_t* geom, ss_stream s) { return ss_fail("ray geometry not built"); }
-extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, uint8_t* rgb, float* depth, float lim, int e0, int ne, ss_stream s) { return ss_fail("ray geometry not built"); }
+
+// ----------------------------------------------------------------------------- device: tracing
+__device__ __forceinline__ void q2m(float* R, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+__device__ __forceinline__ void qmul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+        y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  float n = rsqrtf(w * w + x * x + y * y + z * z);
+  r[0] = w * n; r[1] = x * n; r[2] = y * n; r[3] = z * n;
+}
+
+// world transform (pos[3], rot[9]) of every ray-visible geom of every env
+__global__ void ray_prepare_kernel(RayModel r, int nenv, const float* __restrict__ xpos, const float* __restrict__ xquat,
+                                   float* __restrict__ xf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nenv * r.nraygeom) return;
+  int e = i / r.nraygeom, k = i % r.nraygeom, b = r.rg_body[k];
+  const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+  float Rb[9], q[4], gq[4] = {r.rg_quat[4 * k], r.rg_quat[4 * k + 1], r.rg_quat[4 * k + 2], r.rg_quat[4 * k + 3]};
+  float bqq[4] = {bq[0], bq[1], bq[2], bq[3]};
+  q2m(Rb, bqq);
+  float lp[3] = {r.rg_pos[3 * k], r.rg_pos[3 * k + 1], r.rg_pos[3 * k + 2]};
+  float* o = xf + (size_t)i * 12;
+  o[0] = bp[0] + Rb[0] * lp[0] + Rb[1] * lp[1] + Rb[2] * lp[2];
+  o[1] = bp[1] + Rb[3] * lp[0] + Rb[4] * lp[1] + Rb[5] * lp[2];
+  o[2] = bp[2] + Rb[6] * lp[0] + Rb[7] * lp[1] + Rb[8] * lp[2];
+  qmul(q, bqq, gq);
+  q2m(o + 3, q);
+}
+
+struct Hit { float t; int k; float n[3]; };  // k = index into the ray-geom list; n = local-frame normal (unnormalised)
+
+__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, const float* o, const float* inv, float tmax, float* tnear) {
+  float t0 = 0.f, t1 = tmax;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float l = (k == 0 ? lo.x : k == 1 ? lo.y : lo.z), h = (k == 0 ? hi.x : k == 1 ? hi.y : hi.z);
+    float a = (l - o[k]) * inv[k], b = (h - o[k]) * inv[k];
+    float mn = fminf(a, b), mx = fmaxf(a, b);
+    t0 = fmaxf(t0, mn); t1 = fminf(t1, mx);
+  }
+  *tnear = t0;
+  return t0 <= t1;
+}
+
+__device__ float trace_mesh(const RayModel& r, int root, const float* o, const float* d, float tmin, float tbest, float* nrm) {
+  float inv[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) inv[k] = 1.0f / (fabsf(d[k]) > 1e-20f ? d[k] : (d[k] < 0 ? -1e-20f : 1e-20f));
+  float best = tbest;  // only hits closer than tbest matter (<0: none yet)
+  bool found = false;
+  int stack[40], sp = 0;
+  stack[sp++] = root;
+  while (sp) {
+    int id = stack[--sp];
+    float4 n0 = __ldg(r.bvh + 2 * id), n1 = __ldg(r.bvh + 2 * id + 1);
+    float tn;
+    if (!box_hit(n0, n1, o, inv, best >= 0 ? best : 1e30f, &tn)) continue;
+    int left = __float_as_int(n0.w), right = __float_as_int(n1.w);
+    if (left < 0) {
+      int first = ~left;
+      for (int i = first; i < first + right; i++) {
+        float4 v0 = __ldg(r.tri + 3 * i), e1 = __ldg(r.tri + 3 * i + 1), e2 = __ldg(r.tri + 3 * i + 2);
+        float p[3] = {d[1] * e2.z - d[2] * e2.y, d[2] * e2.x - d[0] * e2.z, d[0] * e2.y - d[1] * e2.x};
+        float det = e1.x * p[0] + e1.y * p[1] + e1.z * p[2];
+        if (fabsf(det) < 1e-30f) continue;
+        float idet = 1.0f / det, t[3] = {o[0] - v0.x, o[1] - v0.y, o[2] - v0.z};
+        float u = (t[0] * p[0] + t[1] * p[1] + t[2] * p[2]) * idet;
+        if (u < 0 || u > 1) continue;
+        float q[3] = {t[1] * e1.z - t[2] * e1.y, t[2] * e1.x - t[0] * e1.z, t[0] * e1.y - t[1] * e1.x};
+        float v = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) * idet;
+        if (v < 0 || u + v > 1) continue;
+        float x = (e2.x * q[0] + e2.y * q[1] + e2.z * q[2]) * idet;
+        if (x >= tmin && (best < 0 || x < best)) {
+          best = x; found = true;
+          nrm[0] = e1.y * e2.z - e1.z * e2.y; nrm[1] = e1.z * e2.x - e1.x * e2.z; nrm[2] = e1.x * e2.y - e1.y * e2.x;
+        }
+      }
+    } else if (sp < 38) {
+      // visit the nearer child first
+      float4 l0 = __ldg(r.bvh + 2 * left), l1 = __ldg(r.bvh + 2 * left + 1), r0 = __ldg(r.bvh + 2 * right), r1 = __ldg(r.bvh + 2 * right + 1);
+      float tl, tr;
+      float lim = best >= 0 ? best : 1e30f;
+      bool hl = box_hit(l0, l1, o, inv, lim, &tl), hr = box_hit(r0, r1, o, inv, lim, &tr);
+      if (hl && hr) {
+        if (tl <= tr) { stack[sp++] = right; stack[sp++] = left; } else { stack[sp++] = left; stack[sp++] = right; }
+      } else if (hl) stack[sp++] = left;
+      else if (hr) stack[sp++] = right;
+    }
+  }
+  return found ? best : -1.f;
+}
+
+// nearest intersection with one geom in its local frame, x >= tmin and (tbest<0 or x<tbest)
+__device__ float trace_geom(const RayModel& r, int k, const float* o, const float* d, float tmin, float tbest, float* nrm) {
+  int type = r.rg_type[k];
+  float s0 = r.rg_size[3 * k], s1 = r.rg_size[3 * k + 1], s2 = r.rg_size[3 * k + 2];
+  if (type == GEOM_PLANE) {
+    if (d[2] > -1e-15f) return -1.f;
+    float x = -o[2] / d[2];
+    if (x < tmin) return -1.f;
+    float px = o[0] + x * d[0], py = o[1] + x * d[1];
+    if ((s0 > 0 && fabsf(px) > s0) || (s1 > 0 && fabsf(py) > s1)) return -1.f;
+    nrm[0] = 0; nrm[1] = 0; nrm[2] = 1;
+    return x;
+  }
+  if (type == GEOM_SPHERE) {
+    float a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], b = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
+    float c = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - s0 * s0, det = b * b - a * c;
+    if (det < 0) return -1.f;
+    float sq = sqrtf(det), x = (-b - sq) / a;
+    if (x < tmin) x = (-b + sq) / a;
+    if (x < tmin) return -1.f;
+    nrm[0] = o[0] + x * d[0]; nrm[1] = o[1] + x * d[1]; nrm[2] = o[2] + x * d[2];
+    return x;
+  }
+  if (type == GEOM_BOX) {
+    float best = -1.f, sz[3] = {s0, s1, s2};
+    for (int ax = 0; ax < 3; ax++) {
+      if (fabsf(d[ax]) < 1e-15f) continue;
+      int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+      for (int sg = -1; sg <= 1; sg += 2) {
+        float t = (sg * sz[ax] - o[ax]) / d[ax];
+        if (t < tmin) continue;
+        if (fabsf(o[a1] + t * d[a1]) <= sz[a1] && fabsf(o[a2] + t * d[a2]) <= sz[a2] && (best < 0 || t < best)) {
+          best = t; nrm[0] = nrm[1] = nrm[2] = 0; nrm[ax] = (float)sg;
+        }
+      }
+    }
+    return best;
+  }
+  if (type == GEOM_CYLINDER) {
+    float best = -1.f;
+    float a = d[0] * d[0] + d[1] * d[1], b = d[0] * o[0] + d[1] * o[1], c = o[0] * o[0] + o[1] * o[1] - s0 * s0, det = b * b - a * c;
+    if (a > 1e-15f && det >= 0) {
+      float sq = sqrtf(det);
+      for (int j = 0; j < 2; j++) {
+        float t = (-b + (j ? sq : -sq)) / a;
+        if (t >= tmin && fabsf(o[2] + t * d[2]) <= s1 && (best < 0 || t < best)) { best = t; nrm[0] = o[0] + t * d[0]; nrm[1] = o[1] + t * d[1]; nrm[2] = 0; }
+      }
+    }
+    if (fabsf(d[2]) > 1e-15f)
+      for (int sg = -1; sg <= 1; sg += 2) {
+        float t = (sg * s1 - o[2]) / d[2];
+        if (t < tmin) continue;
+        float px = o[0] + t * d[0], py = o[1] + t * d[1];
+        if (px * px + py * py <= s0 * s0 && (best < 0 || t < best)) { best = t; nrm[0] = nrm[1] = 0; nrm[2] = (float)sg; }
+      }
+    return best;
+  }
+  if (type == GEOM_MESH) {
+    int root = r.rmesh_bvhadr[r.rg_mesh[k]];
+    if (root < 0) return -1.f;
+    return trace_mesh(r, root, o, d, tmin, tbest, nrm);
+  }
+  return -1.f;
+}
+
+// nearest hit over a list of geoms (indices into the ray-geom table); xf = this env's transforms in
+// shared or global memory, addressed by ray-geom index
+__device__ Hit trace_scene(const RayModel& r, const float* xf, const int* list, int nlist, const float* pnt, const float* vec,
+                           float tmin, int groupmask, int bodyexclude) {
+  Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+  float vv = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
+  for (int i = 0; i < nlist; i++) {
+    int k = list ? list[i] : i;
+    if (r.rg_body[k] == bodyexclude) continue;
+    if (groupmask && !((groupmask >> r.rg_group[k]) & 1)) continue;
+    const float* T = xf + 12 * k;
+    float dif[3] = {pnt[0] - T[0], pnt[1] - T[1], pnt[2] - T[2]};
+    if (r.rg_type[k] != GEOM_PLANE) {
+      float rb = r.rg_rbound[k];
+      float b = vec[0] * dif[0] + vec[1] * dif[1] + vec[2] * dif[2], c = dif[0] * dif[0] + dif[1] * dif[1] + dif[2] * dif[2] - rb * rb;
+      if (c > 0 && (b > 0 || b * b - vv * c < 0)) continue;
+      if (h.t >= 0 && c > 0) {  // sphere entirely beyond the current best hit
+        float tent = (-b - sqrtf(b * b - vv * c)) / vv;
+        if (tent > h.t) continue;
+      }
+    }
+    const float* R = T + 3;
+    float o[3] = {R[0] * dif[0] + R[3] * dif[1] + R[6] * dif[2], R[1] * dif[0] + R[4] * dif[1] + R[7] * dif[2], R[2] * dif[0] + R[5] * dif[1] + R[8] * dif[2]};
+    float d[3] = {R[0] * vec[0] + R[3] * vec[1] + R[6] * vec[2], R[1] * vec[0] + R[4] * vec[1] + R[7] * vec[2], R[2] * vec[0] + R[5] * vec[1] + R[8] * vec[2]};
+    float n[3];
+    float x = trace_geom(r, k, o, d, tmin, h.t, n);
+    if (x >= 0 && (h.t < 0 || x < h.t)) { h.t = x; h.k = k; h.n[0] = n[0]; h.n[1] = n[1]; h.n[2] = n[2]; }
+  }
+  return h;
+}
+
+// ----------------------------------------------------------------------------- lidar
+__global__ void lidar_kernel(RayModel r, int nenv, int nsensordata, const float* __restrict__ xpos, const float* __restrict__ xquat,
+                             const float* __restrict__ xf_all, float* __restrict__ out, float* __restrict__ sensordata) {
+  extern __shared__ float sxf[];
+  int e = blockIdx.x;
+  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
+  for (int i = threadIdx.x; i < r.nraygeom * 12; i += blockDim.x) sxf[i] = xf[i];
+  __syncthreads();
+  for (int s = threadIdx.x; s < r.nrange; s += blockDim.x) {
+    int site = r.range_site[s], b = r.site_bodyid[site];
+    const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+    float Rb[9], q[4], bqq[4] = {bq[0], bq[1], bq[2], bq[3]}, R[9];
+    float sq[4] = {r.site_quat[4 * site], r.site_quat[4 * site + 1], r.site_quat[4 * site + 2], r.site_quat[4 * site + 3]};
+    float sp[3] = {r.site_pos[3 * site], r.site_pos[3 * site + 1], r.site_pos[3 * site + 2]};
+    q2m(Rb, bqq);
+    float p[3] = {bp[0] + Rb[0] * sp[0] + Rb[1] * sp[1] + Rb[2] * sp[2], bp[1] + Rb[3] * sp[0] + Rb[4] * sp[1] + Rb[5] * sp[2],
+                  bp[2] + Rb[6] * sp[0] + Rb[7] * sp[1] + Rb[8] * sp[2]};
+    qmul(q, bqq, sq);
+    q2m(R, q);
+    float dir[3] = {R[2], R[5], R[8]};
+    Hit h = trace_scene(r, sxf, nullptr, r.nraygeom, p, dir, 0.f, 0, b);
+    float dist = h.t;
+    float cut = r.range_cutoff[s];
+    if (dist >= 0 && cut > 0 && dist > cut) dist = cut;
+    if (out) out[(size_t)e * r.nrange + s] = dist;
+    if (sensordata) sensordata[(size_t)e * nsensordata + r.range_adr[s]] = dist;
+  }
+}
+
+__global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restrict__ xf_all, const float* __restrict__ origin,
+                            const float* __restrict__ dir, int groupmask, int bodyexclude, float* __restrict__ dist,
+                            int32_t* __restrict__ geom) {
+  extern __shared__ float sxf[];
+  int e = blockIdx.x;
+  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
+  for (int i = threadIdx.x; i < r.nraygeom * 12; i += blockDim.x) sxf[i] = xf[i];
+  __syncthreads();
+  for (int s = threadIdx.x; s < nray; s += blockDim.x) {
+    size_t k = (size_t)e * nray + s;
+    float p[3] = {origin[3 * k], origin[3 * k + 1], origin[3 * k + 2]}, d[3] = {dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]};
+    Hit h = trace_scene(r, sxf, nullptr, r.nraygeom, p, d, 0.f, groupmask, bodyexclude);
+    dist[k] = h.t;
+    if (geom) geom[k] = h.k >= 0 ? r.rg_geom[h.k] : -1;
+  }
+}
+
+// ----------------------------------------------------------------------------- camera
+#define TILE 16
+__global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env_begin, int cam, int W, int H, float fovy_deg,
+                                                             const float* __restrict__ xpos, const float* __restrict__ xquat,
+                                                             const float* __restrict__ xf_all, uint8_t* __restrict__ rgb,
+                                                             float* __restrict__ depth, float depth_limit) {
+  extern __shared__ float sm[];
+  float* sxf = sm;                                  // [nraygeom*12]
+  int* list = (int*)(sm + r.nraygeom * 12);         // [nraygeom]
+  int* flag = list + r.nraygeom;                    // [nraygeom]
+  __shared__ int nlist;
+  __shared__ float cam_eye[3], cam_R[9];
+  int le = blockIdx.z, e = env_begin + le, tid = threadIdx.y * TILE + threadIdx.x;
+  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
+  for (int i = tid; i < r.nraygeom * 12; i += TILE * TILE) sxf[i] = xf[i];
+  if (tid == 0) {
+    int b = r.cam_bodyid[cam];
+    const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+    float Rb[9], q[4], bqq[4] = {bq[0], bq[1], bq[2], bq[3]};
+    float cq[4] = {r.cam_quat[4 * cam], r.cam_quat[4 * cam + 1], r.cam_quat[4 * cam + 2], r.cam_quat[4 * cam + 3]};
+    float cp[3] = {r.cam_pos[3 * cam], r.cam_pos[3 * cam + 1], r.cam_pos[3 * cam + 2]};
+    q2m(Rb, bqq);
+    cam_eye[0] = bp[0] + Rb[0] * cp[0] + Rb[1] * cp[1] + Rb[2] * cp[2];
+    cam_eye[1] = bp[1] + Rb[3] * cp[0] + Rb[4] * cp[1] + Rb[5] * cp[2];
+    cam_eye[2] = bp[2] + Rb[6] * cp[0] + Rb[7] * cp[1] + Rb[8] * cp[2];
+    qmul(q, bqq, cq);
+    q2m(cam_R, q);
+  }
+  __syncthreads();
+  float f = 0.5f * H / tanf(fovy_deg * 3.14159265358979f / 360.0f);
+  float znear = r.znear * r.extent, zfar = r.zfar * r.extent;
+  // tile frustum culling: geoms whose bounding sphere misses the tile's pyramid are dropped
+  {
+    float x0 = (blockIdx.x * TILE - 0.5f * W) / f, x1 = (fminf((blockIdx.x + 1) * TILE, (float)W) - 0.5f * W) / f;
+    float y0 = -((blockIdx.y * TILE) - 0.5f * H) / f, y1 = -(fminf((blockIdx.y + 1) * TILE, (float)H) - 0.5f * H) / f;  // y0 > y1
+    for (int k = tid; k < r.nraygeom; k += TILE * TILE) {
+      bool keep = true;
+      if (!((0x7 >> r.rg_group[k]) & 1)) keep = false;  // camera sees geom groups 0..2 (collision group 3 hidden)
+      else if (r.rg_type[k] != GEOM_PLANE) {
+        const float* T = sxf + 12 * k;
+        float dw[3] = {T[0] - cam_eye[0], T[1] - cam_eye[1], T[2] - cam_eye[2]};
+        // camera-frame centre (camera looks down -z, +y up)
+        float c[3] = {cam_R[0] * dw[0] + cam_R[3] * dw[1] + cam_R[6] * dw[2], cam_R[1] * dw[0] + cam_R[4] * dw[1] + cam_R[7] * dw[2],
+                      cam_R[2] * dw[0] + cam_R[5] * dw[1] + cam_R[8] * dw[2]};
+        float rb = r.rg_rbound[k];
+        if (-c[2] < znear - rb) keep = false;
+        // side planes through the eye: left (x >= x0*(-z)), right, top, bottom; normals normalised
+        float il = rsqrtf(1 + x0 * x0), ir = rsqrtf(1 + x1 * x1), it = rsqrtf(1 + y0 * y0), ib = rsqrtf(1 + y1 * y1);
+        if ((c[0] + x0 * c[2]) * il < -rb) keep = false;    // left:  x - x0*(-z) >= 0
+        if ((-c[0] - x1 * c[2]) * ir < -rb) keep = false;   // right: x1*(-z) - x >= 0
+        if ((-c[1] - y0 * c[2]) * it < -rb) keep = false;   // top:   y0*(-z) - y >= 0
+        if ((c[1] + y1 * c[2]) * ib < -rb) keep = false;    // bottom
+      }
+      flag[k] = keep;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < r.nraygeom; k++) if (flag[k]) list[n++] = k;
+    nlist = n;
+  }
+  __syncthreads();
+  int u = blockIdx.x * TILE + threadIdx.x, v = blockIdx.y * TILE + threadIdx.y;
+  if (u >= W || v >= H) return;
+  float dl[3] = {(u + 0.5f - 0.5f * W) / f, -(v + 0.5f - 0.5f * H) / f, -1.0f};
+  float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
+                 cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
+  Hit h = trace_scene(r, sxf, list, nlist, cam_eye, dw, znear, 0, -1);
+  float x = h.t;
+  if (x < 0 || x > zfar) { x = zfar; h.k = -1; }
+  size_t pix = ((size_t)le * H + v) * W + u;
+  if (depth) depth[pix] = (depth_limit > 0 && x > depth_limit) ? 0.f : x;   // utils.limit_depth_distance
+  if (rgb) {
+    float col[3];
+    if (h.k < 0) {
+      float inv = rsqrtf(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);
+      float tt = 0.5f * (1.0f + dw[2] * inv);
+      for (int a = 0; a < 3; a++) col[a] = r.nsky >= 2 ? tt * r.sky[a] + (1 - tt) * r.sky[3 + a] : 0.f;
+    } else {
+      const float* sh = r.rg_shade + 8 * h.k;
+      const float* R = sxf + 12 * h.k + 3;
+      float n[3] = {R[0] * h.n[0] + R[1] * h.n[1] + R[2] * h.n[2], R[3] * h.n[0] + R[4] * h.n[1] + R[5] * h.n[2], R[6] * h.n[0] + R[7] * h.n[1] + R[8] * h.n[2]};
+      float inv = rsqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      n[0] *= inv; n[1] *= inv; n[2] *= inv;
+      float pos[3] = {cam_eye[0] + x * dw[0], cam_eye[1] + x * dw[1], cam_eye[2] + x * dw[2]};
+      float vw[3] = {-dw[0], -dw[1], -dw[2]};
+      inv = rsqrtf(vw[0] * vw[0] + vw[1] * vw[1] + vw[2] * vw[2]);
+      vw[0] *= inv; vw[1] *= inv; vw[2] *= inv;
+      if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+      for (int a = 0; a < 3; a++) col[a] = sh[a] * sh[6];
+      float shininess = fmaxf(sh[5] * 128.0f, 1.0f);
+      for (int l = -1; l < r.nlight; l++) {
+        float L[3], amb[3], dif[3], spc[3];
+        if (l < 0) {
+          if (!r.headlight_active) continue;
+          L[0] = cam_R[2]; L[1] = cam_R[5]; L[2] = cam_R[8];   // -forward = +z of the camera frame
+          for (int a = 0; a < 3; a++) { amb[a] = r.headlight[a]; dif[a] = r.headlight[3 + a]; spc[a] = r.headlight[6 + a]; }
+        } else {
+          int b = r.light_bodyid[l];
+          const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+          float Rb[9], bqq[4] = {bq[0], bq[1], bq[2], bq[3]};
+          q2m(Rb, bqq);
+          if (r.light_directional[l]) {
+            const float* ld = r.light_dir + 3 * l;
+            L[0] = -(Rb[0] * ld[0] + Rb[1] * ld[1] + Rb[2] * ld[2]); L[1] = -(Rb[3] * ld[0] + Rb[4] * ld[1] + Rb[5] * ld[2]);
+            L[2] = -(Rb[6] * ld[0] + Rb[7] * ld[1] + Rb[8] * ld[2]);
+          } else {
+            const float* lp = r.light_pos + 3 * l;
+            L[0] = bp[0] + Rb[0] * lp[0] + Rb[1] * lp[1] + Rb[2] * lp[2] - pos[0];
+            L[1] = bp[1] + Rb[3] * lp[0] + Rb[4] * lp[1] + Rb[5] * lp[2] - pos[1];
+            L[2] = bp[2] + Rb[6] * lp[0] + Rb[7] * lp[1] + Rb[8] * lp[2] - pos[2];
+          }
+          float il = rsqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+          L[0] *= il; L[1] *= il; L[2] *= il;
+          for (int a = 0; a < 3; a++) { amb[a] = r.light_ambient[3 * l + a]; dif[a] = r.light_diffuse[3 * l + a]; spc[a] = r.light_specular[3 * l + a]; }
+        }
+        float nl = fmaxf(n[0] * L[0] + n[1] * L[1] + n[2] * L[2], 0.f), hs = 0.f;
+        if (nl > 0) {
+          float hv[3] = {L[0] + vw[0], L[1] + vw[1], L[2] + vw[2]};
+          float ih = rsqrtf(hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2]);
+          hs = powf(fmaxf((n[0] * hv[0] + n[1] * hv[1] + n[2] * hv[2]) * ih, 0.f), shininess);
+        }
+        for (int a = 0; a < 3; a++) col[a] += sh[a] * (amb[a] + dif[a] * nl) + sh[4] * spc[a] * hs;
+      }
+    }
+    uint8_t* px = rgb + 3 * pix;
+    for (int a = 0; a < 3; a++) px[a] = (uint8_t)(fminf(fmaxf(col[a], 0.f), 1.f) * 255.0f + 0.5f);
+  }
+}
+
+// ----------------------------------------------------------------------------- C ABI
+static int prepare(ss_batch* B, cudaStream_t st) {
+  const RayModel& r = B->model->rm;
+  if (!r.present) return ss_fail("the model was compiled without ray geometry (compile with with_render=True)");
+  if (!B->bufs.xpos || !B->bufs.xquat) return ss_fail("ray casting needs the xpos/xquat buffers");
+  cudaSetDevice(B->model->device);
+  if (!B->ray_xf) {
+    CUDA_OK(cudaMalloc((void**)&B->ray_xf, (size_t)B->nenv * r.nraygeom * 12 * sizeof(float)));
+  }
+  int n = B->nenv * r.nraygeom;
+  ray_prepare_kernel<<<(n + 255) / 256, 256, 0, st>>>(r, B->nenv, B->bufs.xpos, B->bufs.xquat, B->ray_xf);
+  B->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ss_batch_lidar(ss_batch* B, float* out_dev, ss_stream s) {
+  if (!B) return ss_fail("ss_batch_lidar: null batch");
+  cudaStream_t st = (cudaStream_t)s;
+  if (prepare(B, st) != 0) return -1;
+  const RayModel& r = B->model->rm;
+  if (r.nrange == 0) return ss_fail("model has no rangefinder sensors");
+  size_t smem = (size_t)r.nraygeom * 12 * sizeof(float);
+  cudaFuncSetAttribute(lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  lidar_kernel<<<B->nenv, 128, smem, st>>>(r, B->nenv, B->dm.nsensordata, B->bufs.xpos, B->bufs.xquat, B->ray_xf, out_dev,
+                                           out_dev ? nullptr : B->bufs.sensordata);
+  B->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ss_batch_rays(ss_batch* B, int nray, const float* origin, const float* dir, int groupmask, int bodyexclude,
+                             float* dist, int32_t* geom, ss_stream s) {
+  if (!B || !origin || !dir || !dist || nray <= 0) return ss_fail("ss_batch_rays: bad argument");
+  cudaStream_t st = (cudaStream_t)s;
+  if (prepare(B, st) != 0) return -1;
+  const RayModel& r = B->model->rm;
+  size_t smem = (size_t)r.nraygeom * 12 * sizeof(float);
+  cudaFuncSetAttribute(rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rays_kernel<<<B->nenv, 128, smem, st>>>(r, B->nenv, nray, B->ray_xf, origin, dir, groupmask, bodyexclude, dist, geom);
+  B->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, uint8_t* rgb, float* depth, float depth_limit,
+                               int env_begin, int env_count, ss_stream s) {
+  if (!B || W <= 0 || H <= 0 || (!rgb && !depth)) return ss_fail("ss_batch_render: bad argument");
+  const RayModel& r = B->model->rm;
+  if (r.present && (cam < 0 || cam >= r.ncam)) return ss_fail("ss_batch_render: camera %d out of range", cam);
+  if (env_begin < 0 || env_count <= 0 || env_begin + env_count > B->nenv) return ss_fail("ss_batch_render: env range out of bounds");
+  cudaStream_t st = (cudaStream_t)s;
+  if (prepare(B, st) != 0) return -1;
+  if (fovy <= 0) fovy = B->model->cam_fovy_host[cam];
+  size_t smem = (size_t)r.nraygeom * (12 * sizeof(float) + 2 * sizeof(int));
+  cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, env_count), block(TILE, TILE);
+  if (grid.z > 65535) return ss_fail("ss_batch_render: at most 65535 envs per call");
+  render_kernel<<<grid, block, smem, st>>>(r, env_begin, cam, W, H, fovy, B->bufs.xpos, B->bufs.xquat, B->ray_xf, rgb, depth, depth_limit);
+  B->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -44,6 +44,9 @@ def load_obj(path: str):
                     face_tc.append((tidx[0], tidx[k], tidx[k + 1]))
     v = np.asarray(verts, dtype=np.float64).reshape(-1, 3)
     f = np.asarray(faces, dtype=np.int32).reshape(-1, 3)
+    # CAD exports repeat every vertex once per incident face: merge exact duplicates
+    v, inv = np.unique(v, axis=0, return_inverse=True)
+    f = inv.reshape(-1)[f].astype(np.int32)
     if tcs and f.size and np.all(np.asarray(face_tc) >= 0):
         return v, f, np.asarray(tcs, dtype=np.float64), np.asarray(face_tc, dtype=np.int32)
     return v, f, None, None

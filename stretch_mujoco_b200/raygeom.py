@@ -1,0 +1,70 @@
+"""Ray-visible geometry of a compiled model: what the lidar (<rangefinder>, row S2) and the
+camera (row C3) can hit.
+
+[upstream] mj_ray semantics restated in SURVEY.md Appendix B: every geom is a candidate regardless
+of group or contype, geoms whose rgba (or material) alpha is 0 are skipped, meshes are intersected
+as TRIANGLE meshes (not hulls).  A collision-class geom that is an exact copy of a visual geom
+(same body, mesh and pose -- most of `stretch.xml`'s collision meshes) produces identical hits and
+is dropped here so that it is not traversed twice.
+
+Arrays added to the model (consumed by csrc/rays.cu and by the oracle):
+  raygeom_id[n]            geom ids that rays test
+  geom_shade[ngeom, 8]     rgb, alpha, specular, shininess, emission, reflectance
+  rmesh_vertadr/faceadr/facenum[nmesh], rmesh_vert[*,3] f32, rmesh_face[*,3] i32 (mesh frame)
+Acceleration structures (BVHs) are built at load time by each consumer.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mjcf import _floats
+
+
+def build_ray_geometry(m, verbose: bool = False) -> None:
+    A = m.arrays
+    sc = m.scene
+    ngeom = len(A["geom_type"])
+    # per-geom shading parameters (geom rgba overrides the material colour when given explicitly)
+    shade = np.zeros((ngeom, 8))
+    flat_geoms = [g for b in sc.bodies for g in b.geoms]
+    for gi, g in enumerate(flat_geoms):
+        rgba = A["geom_rgba"][gi]
+        spec, shin, emis, refl = 0.5, 0.5, 0.0, 0.0
+        mat = g.get("material")
+        if mat:
+            mt = sc.materials[mat]
+            spec, shin, emis, refl = float(mt["specular"]), float(mt["shininess"]), float(mt["emission"]), float(mt["reflectance"])
+        shade[gi] = [rgba[0], rgba[1], rgba[2], rgba[3], spec, shin, emis, refl]
+    A["geom_shade"] = shade
+    # candidate list with duplicate suppression
+    keep = []
+    seen = {}
+    order = sorted(range(ngeom), key=lambda g: (A["geom_group"][g] > 2, g))  # visual copies win over collision copies
+    for g in order:
+        if shade[g, 3] == 0:
+            continue
+        if A["geom_type"][g] == 7:
+            key = (int(A["geom_bodyid"][g]), int(A["geom_dataid"][g]), tuple(np.round(A["geom_pos"][g], 9)),
+                   tuple(np.round(A["geom_quat"][g], 9)))
+            if key in seen:
+                continue
+            seen[key] = g
+        keep.append(g)
+    keep.sort()
+    A["raygeom_id"] = np.asarray(keep, dtype=np.int32)
+    # triangle soups of the meshes referenced by kept geoms
+    nmesh = len(m.mesh_assets)
+    used = sorted({int(A["geom_dataid"][g]) for g in keep if A["geom_type"][g] == 7})
+    vertadr = -np.ones(nmesh, np.int32); faceadr = -np.ones(nmesh, np.int32); facenum = np.zeros(nmesh, np.int32)
+    verts, faces = [], []
+    nv = nf = 0
+    for mid in used:
+        ma = m.mesh_assets[mid]
+        vertadr[mid], faceadr[mid], facenum[mid] = nv, nf, len(ma.faces)
+        verts.append(ma.verts.astype(np.float32)); faces.append(ma.faces.astype(np.int32))
+        nv += len(ma.verts); nf += len(ma.faces)
+    A["rmesh_vertadr"], A["rmesh_faceadr"], A["rmesh_facenum"] = vertadr, faceadr, facenum
+    A["rmesh_vert"] = np.concatenate(verts) if verts else np.zeros((0, 3), np.float32)
+    A["rmesh_face"] = np.concatenate(faces) if faces else np.zeros((0, 3), np.int32)
+    if verbose:
+        print(f"ray geometry: {len(keep)} of {ngeom} geoms, {len(used)} meshes, {nf} triangles, {nv} vertices")

@@ -19,3 +19,9 @@ if __name__ == "__main__":
     m = scenes.compile_default_scene(with_render=False)
     blob.save(os.path.join(HERE, "stretch_default_scene.ssm"), m)
     print("default scene:", m.sizes)
+    # with ray geometry (triangle soups of every ray-visible mesh), zlib-compressed
+    m = scenes.compile_empty_floor(with_render=True)
+    blob.save(os.path.join(HERE, "stretch_empty_floor_render.ssm.z"), m)
+    m = scenes.compile_default_scene(with_render=True)
+    blob.save(os.path.join(HERE, "stretch_default_scene_render.ssm.z"), m)
+    print("render blobs: %d ray geoms, %d triangles" % (len(m.raygeom_id), len(m.rmesh_face)))

@@ -1,0 +1,204 @@
+"""Parity of the CUDA physics path (through the C ABI) against the fp64 CPU oracle.  GPU only.
+
+Tolerances (fp32 device vs fp64 oracle, stated per test):
+  * single forward pass: mass matrix 1e-5 rel, contact pair list bit-exact, contact distance 1e-6 m,
+    joint-space constraint force 1e-3 rel;
+  * 1000-step rollouts from the settled `home` pose with per-env random targets: envs whose whole
+    rollout has only plane contacts (wheels, caster) must agree to 1e-4 relative in qpos
+    (north-star bar); envs that enter convex mesh contact (single-point MPR contacts are
+    discontinuous in the configuration) are bounded statistically.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(blob_empty_floor):
+    from stretch_mujoco_b200 import engine
+    return engine.DeviceModel(blob_empty_floor, 0)
+
+
+def _targets(rng, home, nenv):
+    ctrl = np.tile(home, (nenv, 1))
+    ctrl[:, 0:2] = rng.uniform(-3, 3, (nenv, 2)); ctrl[:, 2] = rng.uniform(0.3, 1.0, nenv); ctrl[:, 3] = rng.uniform(0, 0.4, nenv)
+    ctrl[:, 4] = rng.uniform(-1, 3, nenv); ctrl[:, 5] = rng.uniform(-1, 0.5, nenv); ctrl[:, 6] = rng.uniform(-2, 2, nenv)
+    ctrl[:, 7] = rng.uniform(-0.02, 0.04, nenv); ctrl[:, 8] = rng.uniform(-3, 1.5, nenv); ctrl[:, 9] = rng.uniform(-1.4, 0.7, nenv)
+    ctrl[0] = home
+    return ctrl
+
+
+def _load(B, qpos, qvel, warm, ctrl):
+    B.qpos.copy_(torch.tensor(qpos, dtype=torch.float32)); B.qvel.copy_(torch.tensor(qvel, dtype=torch.float32))
+    B.qacc_warmstart.copy_(torch.tensor(warm, dtype=torch.float32)); B.ctrl.copy_(torch.tensor(ctrl, dtype=torch.float32))
+    B.time.zero_(); B.env_flags.zero_()
+    f = lambda t: t.cpu().numpy().astype(np.float64)
+    return f(B.qpos), f(B.qvel), f(B.qacc_warmstart), f(B.ctrl)  # fp32-rounded copies for the oracle
+
+
+def test_forward_matches_oracle_at_qpos0(gpu, oracle_E, arrays_E):
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    nenv = 32
+    rng = np.random.default_rng(0)
+    B = engine.Batch(gpu, nenv, debug=True)
+    lo, hi = A["actuator_ctrlrange"][:, 0], A["actuator_ctrlrange"][:, 1]
+    ctrl = rng.uniform(lo, hi, size=(nenv, gpu.nu))
+    qpos, qvel, warm, ctrl = _load(B, np.tile(A["qpos0"], (nenv, 1)), rng.normal(scale=0.05, size=(nenv, gpu.nv)),
+                                   np.zeros((nenv, gpu.nv)), ctrl)
+    B.forward(); torch.cuda.synchronize()
+    o = oracle_E.forward(qpos, qvel, ctrl, warm, maxcon=B.maxcon,
+                         want=("M", "qacc_smooth", "ncon", "nefc", "contact_geom", "contact_dist", "qfrc_constraint", "qacc"))
+    M = B.dbg["M"].cpu().numpy()
+    assert np.abs(M - o["M"]).max() <= 1e-5 * np.abs(o["M"]).max()
+    assert np.array_equal(B.ncon.cpu().numpy(), o["ncon"])
+    assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])          # bit-exact pair indexing
+    assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
+    assert np.abs(B.contact_dist.cpu().numpy() - o["contact_dist"]).max() < 1e-6
+    qs = B.dbg["qacc_smooth"].cpu().numpy()
+    assert np.abs(qs - o["qacc_smooth"]).max() <= 1e-3 * np.abs(o["qacc_smooth"]).max()
+    fc = B.dbg["qfrc_constraint"].cpu().numpy()
+    assert np.abs(fc - o["qfrc_constraint"]).max() <= 1e-3 * np.abs(o["qfrc_constraint"]).max()
+
+
+def test_forward_matches_oracle_from_home(gpu, oracle_E, arrays_E, settled_home_E):
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    nenv = 64
+    rng = np.random.default_rng(1)
+    q0, v0, w0, home = settled_home_E
+    B = engine.Batch(gpu, nenv, debug=True)
+    qpos = np.tile(q0, (nenv, 1)); qpos[:, 7:] += rng.normal(scale=0.01, size=(nenv, gpu.nq - 7))
+    qpos, qvel, warm, ctrl = _load(B, qpos, np.tile(v0, (nenv, 1)) + rng.normal(scale=0.02, size=(nenv, gpu.nv)),
+                                   np.tile(w0, (nenv, 1)), _targets(rng, home, nenv))
+    B.forward(); torch.cuda.synchronize()
+    o = oracle_E.forward(qpos, qvel, ctrl, warm, maxcon=B.maxcon, want=("ncon", "contact_geom", "qfrc_constraint", "qacc", "nefc"))
+    assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])
+    assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
+    fc = B.dbg["qfrc_constraint"].cpu().numpy()
+    rel = np.abs(fc - o["qfrc_constraint"]).max(axis=1) / np.abs(o["qfrc_constraint"]).max(axis=1)
+    assert np.median(rel) < 1e-4 and rel.max() < 5e-3
+    # one full step (implicitfast) from the same states: velocities agree to 2e-4 rad/s (fp32 noise on the
+    # 8e-7 kg m^2 rubber-tip joints dominates), positions to 1e-6
+    B.step(1); torch.cuda.synchronize()
+    oracle_E.step(qpos, qvel, ctrl, warm, nsteps=1)
+    dv = np.abs(B.qvel.cpu().numpy() - qvel).max(axis=1)
+    assert np.median(dv) < 1e-4 and dv.max() < 5e-4
+    assert np.abs(B.qpos.cpu().numpy() - qpos).max() < 2e-6
+
+
+def test_rollout_1000_steps_from_home(gpu, oracle_E, arrays_E, settled_home_E):
+    """64 envs x 1000 steps, per-env random arm/wrist/head targets and gentle base motion.
+    Contact activation is a discontinuity of the dynamics (a wheel that touches at -1e-9 m in
+    fp64 and misses at +1e-9 m in fp32 changes the next step), so the 1e-4 bar is asserted for
+    every env whose contact list agreed at all 100 checkpoints, and those must be the bulk."""
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    nenv = 64
+    rng = np.random.default_rng(0)
+    q0, v0, w0, home = settled_home_E
+    B = engine.Batch(gpu, nenv)
+    tg = _targets(rng, home, nenv)
+    tg[:, 0:2] = rng.uniform(-0.5, 0.5, (nenv, 2)); tg[:, 7] = rng.uniform(0.0, 0.04, nenv)
+    qpos, qvel, warm, ctrl = _load(B, np.tile(q0, (nenv, 1)), np.tile(v0, (nenv, 1)), np.tile(w0, (nenv, 1)), tg)
+    t = np.zeros(nenv)
+    pairs_equal = np.ones(nenv, bool)
+    for k in range(100):
+        B.step(10); torch.cuda.synchronize()
+        o = oracle_E.step(qpos, qvel, ctrl, warm, t, nsteps=10, maxcon=B.maxcon, want=("contact_geom", "flags"))
+        pairs_equal &= np.all(B.contact_geom.cpu().numpy() == o["contact_geom"], axis=(1, 2))
+    err = np.abs(B.qpos.cpu().numpy() - qpos)
+    rel = (err / np.maximum(np.abs(qpos), 1.0)).max(axis=1)
+    print("rollout parity: pairs always equal in %d/%d envs; rel qpos err median %.2e, max over matching envs %.2e, max %.2e"
+          % (pairs_equal.sum(), nenv, np.median(rel), rel[pairs_equal].max(), rel.max()))
+    assert pairs_equal.sum() >= int(0.85 * nenv)
+    assert rel[pairs_equal].max() < 1e-4, f"max rel qpos error {rel[pairs_equal].max():.2e}"
+    assert np.median(rel) < 1e-4 and rel.max() < 5e-2
+    assert float(B.time[0]) == pytest.approx(2.0, abs=1e-4)
+    assert int(B.env_flags.max()) == 0 and int(o["flags"].max()) == 0
+
+
+def test_bad_state_guard_resets_env(gpu, arrays_E):
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    B = engine.Batch(gpu, 4)
+    B.qvel[2, 8] = float("nan")
+    B.qpos[3, 0] = 1e12
+    B.step(1); torch.cuda.synchronize()
+    flags = B.env_flags.cpu().numpy()
+    assert flags[0] == 0 and flags[1] == 0 and flags[2] & 1 and flags[3] & 1
+    assert torch.isfinite(B.qpos).all() and torch.isfinite(B.qvel).all()
+    assert np.abs(B.qpos[3].cpu().numpy() - A["qpos0"]).max() < 0.05
+
+
+def test_reset_and_keyframe(gpu, arrays_E):
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    B = engine.Batch(gpu, 8)
+    B.step(10)
+    mask = torch.zeros(8, dtype=torch.int32, device="cuda"); mask[1] = 1; mask[5] = 1
+    B.reset(mask, key=1)  # stow
+    torch.cuda.synchronize()
+    assert np.allclose(B.ctrl[1].cpu().numpy(), A["key_ctrl"][1]) and np.allclose(B.ctrl[0].cpu().numpy(), 0)
+    assert np.allclose(B.qpos[5].cpu().numpy(), A["qpos0"], atol=1e-6) and float(B.time[5]) == 0.0 and float(B.time[0]) > 0
+
+
+def test_determinism(gpu):
+    from stretch_mujoco_b200 import engine
+    outs = []
+    for _ in range(2):
+        B = engine.Batch(gpu, 16)
+        B.reset(key=0); B.step(200); torch.cuda.synchronize()
+        outs.append(B.qpos.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_status_and_commands_follow_reference_semantics(gpu, arrays_E):
+    """P1/P2 rows: pull_status / push_command / BaseController (mujoco_server.py:93-176,465-578)."""
+    from stretch_mujoco_b200.simulator import StretchMujocoSimulator
+    A, _ = arrays_E
+    sim = StretchMujocoSimulator(model=gpu, nenv=4)
+    with pytest.raises(ConnectionError):
+        sim.pull_status()
+    sim.start()
+    with pytest.raises(Exception):
+        sim.move_to("base_translate", 0.1)
+    with pytest.raises(Exception):
+        sim.move_by("left_wheel_vel", 0.1)
+    sim.step(1500)
+    s = sim.pull_status()
+    assert float(s.time[0]) == pytest.approx(3.0, abs=1e-3)
+    assert float(s.lift.pos[0]) == pytest.approx(0.589, abs=3e-3) and float(s.arm.pos[0]) == pytest.approx(0.1, abs=1e-3)
+    assert float(s.gripper.pos[0]) == pytest.approx(-0.064, abs=2e-3)   # sim 0 -> real range (config.py:4-5)
+    # move_to with per-env targets, move_by relative to the current length, gripper in the real range
+    sim.move_to("lift", torch.tensor([0.4, 0.5, 0.7, 0.8]))
+    sim.move_by("arm", 0.1)
+    sim.move_to("gripper", 0.56, env_ids=torch.tensor([1]))
+    sim.step(1)
+    c = sim.batch.ctrl.cpu().numpy()
+    assert np.allclose(c[:, 2], [0.4, 0.5, 0.7, 0.8]) and np.allclose(c[:, 3], 0.2, atol=2e-3)
+    assert c[1, 7] == pytest.approx(0.04, abs=1e-6) and c[0, 7] == pytest.approx(0.0, abs=1e-6)
+    assert float(sim.batch.command[:, :44].abs().sum()) == 0.0           # triggers are consumed
+    assert sim.wait_until_at_setpoint("lift", timeout=8.0)
+    # set_base_velocity -> wheel ctrl through diff-drive inverse kinematics; status reports it back
+    sim.set_base_velocity(0.1, 0.0)
+    sim.step(500)
+    c = sim.batch.ctrl.cpu().numpy()
+    assert np.allclose(c[:, 0:2], 0.1 / 0.0508, atol=1e-4)
+    s = sim.pull_status()
+    assert float(s.base.x_vel[0]) == pytest.approx(0.1, abs=0.02)        # gear=3 quirk: reported = commanded
+    # base_translate by +0.05 m: closed loop runs at 0.3 m/s until the displacement is reached, then stops
+    x0 = s.base.x.clone(); y0 = s.base.y.clone()
+    sim.move_by("base_translate", 0.05)
+    for _ in range(400):
+        sim.step(5)
+        if float(sim.batch.base_state[:, 0].abs().sum()) == 0:
+            break
+    s = sim.pull_status()
+    d = torch.sqrt((s.base.x - x0) ** 2 + (s.base.y - y0) ** 2)
+    assert float(sim.batch.base_state[:, 0].abs().sum()) == 0 and torch.all(d >= 0.05) and torch.all(d < 0.08)
+    assert np.allclose(sim.batch.ctrl[:, 0:2].cpu().numpy(), 0.0)
+    sim.stop()
+    assert not sim.is_running()

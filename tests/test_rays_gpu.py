@@ -1,0 +1,150 @@
+"""Lidar (S2/L1) and camera (C1-C4) parity against the CPU oracle, through the C ABI.  GPU only.
+
+Tolerances: ray distance / depth 1e-4 relative (fp32 device vs fp64 oracle) on at least 99.5% of the
+rays; the remainder are silhouette rays where a 1e-7 perturbation selects a different surface.
+RGB within +-2 LSB on 99% of the pixels (same shading model on both sides).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob, engine
+    raw = blob.read_bytes(os.path.join(GOLDEN, "stretch_default_scene_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    return dict(raw=raw, A=A, names=names, om=OracleModel(raw), dm=engine.DeviceModel(raw, 0))
+
+
+@pytest.fixture(scope="module")
+def posed(scene):
+    """4 envs: home pose, base rotated / translated, arm raised and extended."""
+    from stretch_mujoco_b200 import engine
+    A, dm = scene["A"], scene["dm"]
+    B = engine.Batch(dm, 4)
+    q = np.tile(A["qpos0"], (4, 1))
+    q[:, 8 + 2] = 0.6                                   # lift (qpos index 7.. are robot joints; lift is joint 3 -> qpos 9)
+    q[1, 0:2] = [0.3, -0.1]; ang = 0.7; q[1, 3:7] = [np.cos(ang / 2), 0, 0, np.sin(ang / 2)]
+    q[2, 0:2] = [-0.2, 0.2]; ang = -2.0; q[2, 3:7] = [np.cos(ang / 2), 0, 0, np.sin(ang / 2)]
+    q[3, 9] = 0.9; q[3, 10:14] = 0.1
+    B.qpos.copy_(torch.tensor(q, dtype=torch.float32))
+    B.forward(); torch.cuda.synchronize()
+    return B
+
+
+def _frac_close(a, b, rtol):
+    ok = np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-3)
+    return ok.mean()
+
+
+def test_lidar_matches_oracle_and_table_kat(scene, posed):
+    B, om = posed, scene["om"]
+    assert scene["dm"].nrange == 360
+    dist = B.lidar().cpu().numpy()
+    xpos, xquat = B.xpos.cpu().numpy().astype(np.float64), B.xquat.cpu().numpy().astype(np.float64)
+    # oracle rays from the same site frames (replicates mj_sensorPos for <rangefinder>)
+    A = scene["A"]
+    names = scene["names"][3]
+    sid = [names.index(f"lidar{i:03d}") for i in range(360)]
+    b = A["site_bodyid"][sid[0]]
+    from stretch_mujoco_b200.mjcf import quat2mat, quat_mul
+    org = np.zeros((4, 360, 3)); dr = np.zeros((4, 360, 3))
+    for e in range(4):
+        Rb = quat2mat(xquat[e, b])
+        for i, s in enumerate(sid):
+            org[e, i] = xpos[e, b] + Rb @ A["site_pos"][s]
+            dr[e, i] = quat2mat(quat_mul(xquat[e, b], A["site_quat"][s]))[:, 2]
+    ref, _ = om.rays(xpos, xquat, org, dr, groupmask=0, bodyexclude=int(b))
+    ref = np.where(ref > 10.0, 10.0, ref)                # cutoff="10.0" (stretch.xml:540)
+    assert ((dist < 0) == (ref < 0)).mean() > 0.995      # misses are -1 (docs/getting_started.ipynb cell 18)
+    hit = (dist >= 0) & (ref >= 0)
+    assert hit.sum() > 300 and _frac_close(dist[hit], ref[hit], 1e-4) > 0.995
+    # env 0 (base at the origin): ray 90 points to the robot's right (-y); the table's near face is the
+    # plane y = -0.5 (scene.xml:24-26) -> rays 92..100 read (0.5 - y_laser)/cos(angle)
+    for i in (93, 95, 100):
+        ang = np.deg2rad(i - 90)
+        assert dist[0, i] == pytest.approx(0.5 / np.cos(ang), abs=2e-3)
+    assert dist.max() <= 10.0
+    # same values land in sensordata when no output buffer is given
+    from stretch_mujoco_b200 import engine
+    engine._check(engine.lib().ss_batch_lidar(B._h, None, engine._stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(B.sensordata[:, 6:366].cpu().numpy(), dist)
+
+
+def test_generic_rays_report_geom_ids(scene, posed):
+    B = posed
+    o = torch.tensor([[[0.0, -1.0, 2.0], [5.0, 5.0, 1.0]]] * 4, device="cuda")
+    d = torch.tensor([[[0.0, 0.0, -1.0], [0.0, 0.0, -1.0]]] * 4, device="cuda")
+    dist, geom = B.rays(o, d)
+    torch.cuda.synchronize()
+    gn = scene["names"][2]
+    assert dist[0, 0].item() == pytest.approx(2.0 - 0.48, abs=1e-5)   # table top at z = 0.48
+    assert dist[0, 1].item() == pytest.approx(1.0, abs=1e-5) and gn[geom[0, 1].item()] == "floor"
+
+
+@pytest.mark.parametrize("cam_name,W,H,fovy", [("d435i_camera_depth", 212, 120, 42.0), ("d405_depth", 240, 135, 58.0),
+                                               ("nav_camera_rgb", 200, 150, 102.0)])
+def test_depth_and_rgb_match_oracle(scene, posed, cam_name, W, H, fovy):
+    B, om, dm = posed, scene["om"], scene["dm"]
+    from stretch_mujoco_b200 import engine
+    cam = dm.name2id(engine.OBJ_CAMERA, cam_name)
+    rgb = torch.zeros(4, H, W, 3, dtype=torch.uint8, device="cuda"); depth = torch.zeros(4, H, W, device="cuda")
+    B.render(cam, W, H, fovy, rgb, depth)
+    torch.cuda.synchronize()
+    xpos, xquat = B.xpos.cpu().numpy().astype(np.float64), B.xquat.cpu().numpy().astype(np.float64)
+    rrgb, rdepth = om.render(xpos, xquat, cam, W, H, fovy)
+    d, c = depth.cpu().numpy(), rgb.cpu().numpy()
+    assert _frac_close(d, rdepth, 1e-4) > 0.995
+    assert (np.abs(c.astype(int) - rrgb.astype(int)).max(axis=-1) <= 2).mean() > 0.99
+    assert d.min() >= 0.012 - 1e-6 and d.max() <= 60.0 + 1e-3      # znear/zfar * extent (scene.xml:5)
+    assert len(np.unique(c.reshape(-1, 3), axis=0)) > 50           # an actual image, not a constant
+
+
+def test_depth_limit_and_camera_intrinsics(scene, posed):
+    B, dm = posed, scene["dm"]
+    from stretch_mujoco_b200 import engine, enums
+    cam = dm.name2id(engine.OBJ_CAMERA, "d405_depth")
+    d0 = torch.zeros(4, 54, 96, device="cuda"); d1 = torch.zeros(4, 54, 96, device="cuda")
+    B.render(cam, 96, 54, 58.0, None, d0, 0.0)
+    B.render(cam, 96, 54, 58.0, None, d1, 1.0)                     # d405 limit 1 m (config.py:8)
+    torch.cuda.synchronize()
+    a, b = d0.cpu().numpy(), d1.cpu().numpy()
+    assert np.array_equal(b, np.where(a > 1.0, 0.0, a))            # utils.limit_depth_distance
+    K = enums.compute_K(42, 1920, 1080)
+    assert K[0, 0] == pytest.approx(0.5 * 1080 / np.tan(np.deg2rad(21)), rel=1e-12) and K[0, 2] == 960
+    assert enums.StretchCameras.cam_nav_rgb.value.fovy == 102
+
+
+def test_default_scene_physics_forward_parity(scene):
+    """nv = 44 (> 32 lanes): robot + dock + two free objects, default scene.xml."""
+    from stretch_mujoco_b200 import engine
+    A, om, dm = scene["A"], scene["om"], scene["dm"]
+    om.set_options(enable_lidar=False)
+    nenv = 8
+    B = engine.Batch(dm, nenv, debug=True, maxcon=32)
+    B.reset(key=0)
+    rng = np.random.default_rng(5)
+    qvel = rng.normal(scale=0.02, size=(nenv, dm.nv))
+    B.qvel.copy_(torch.tensor(qvel, dtype=torch.float32))
+    qpos = B.qpos.cpu().numpy().astype(np.float64); qvel = B.qvel.cpu().numpy().astype(np.float64)
+    ctrl = B.ctrl.cpu().numpy().astype(np.float64)
+    B.forward(); torch.cuda.synchronize()
+    o = om.forward(qpos, qvel, ctrl, None, maxcon=32, want=("M", "contact_geom", "nefc", "qfrc_constraint", "qacc_smooth"))
+    M = B.dbg["M"].cpu().numpy()
+    assert np.abs(M - o["M"]).max() <= 1e-5 * np.abs(o["M"]).max()
+    assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])
+    assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
+    qs = B.dbg["qacc_smooth"].cpu().numpy()
+    assert np.abs(qs - o["qacc_smooth"]).max() <= 1e-3 * np.abs(o["qacc_smooth"]).max()
+    # 200 steps: objects fall on the table, robot homes; no env may blow up
+    B.step(200); torch.cuda.synchronize()
+    assert torch.isfinite(B.qpos).all() and int((B.env_flags & 1).max()) == 0
