@@ -1180,7 +1180,7 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     __syncwarp();
     eval_constraints<true>(m, S, ns, nefc, ncon, 0.f, cost, dg, dh, lane);
   }
-  int iter = 0;
+  int iter = 0;  // `cost` = total objective (Gauss term is zero at qacc_smooth, included in cw)
   while (true) {
     // gradient
     mul_JT(m, S, qfc, force, ns, nefc, lane);
@@ -1233,8 +1233,20 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
     for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
     __syncwarp();
+    float oldcost = cost;
     eval_constraints<true>(m, S, ns, nefc, ncon, 0.f, cost, dg, dh, lane);
+    {
+      float gsum = 0;
+      for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
+      cost += warp_sum(gsum);
+    }
     iter++;
+    // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
+    if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
+      mul_JT(m, S, qfc, force, ns, nefc, lane);
+      __syncwarp();
+      break;
+    }
   }
   return iter;
 }

@@ -64,9 +64,14 @@ def test_lidar_matches_oracle_and_table_kat(scene, posed):
             dr[e, i] = quat2mat(quat_mul(xquat[e, b], A["site_quat"][s]))[:, 2]
     ref, _ = om.rays(xpos, xquat, org, dr, groupmask=0, bodyexclude=int(b))
     ref = np.where(ref > 10.0, 10.0, ref)                # cutoff="10.0" (stretch.xml:540)
-    assert ((dist < 0) == (ref < 0)).mean() > 0.995      # misses are -1 (docs/getting_started.ipynb cell 18)
-    hit = (dist >= 0) & (ref >= 0)
-    assert hit.sum() > 300 and _frac_close(dist[hit], ref[hit], 1e-4) > 0.995
+    # The lidar plane is exactly level here, so a ray direction with z = -1e-8 (fp32) grazes the infinite
+    # floor plane beyond the 10 m cutoff while z = 0 (fp64) misses: "miss" (-1, docs/getting_started.ipynb
+    # cell 18) and "cutoff" are the same reading for this comparison; every nearer hit must agree.
+    assert (dist < 0).sum() > 0 and (ref < 0).sum() > 0
+    dc, rc = np.where(dist < 0, 10.0, dist), np.where(ref < 0, 10.0, ref)
+    assert ((dc < 10.0) == (rc < 10.0)).mean() > 0.995
+    hit = (dc < 10.0) & (rc < 10.0)
+    assert hit.sum() > 300 and _frac_close(dc[hit], rc[hit], 1e-4) > 0.995
     # env 0 (base at the origin): ray 90 points to the robot's right (-y); the table's near face is the
     # plane y = -0.5 (scene.xml:24-26) -> rays 92..100 read (0.5 - y_laser)/cos(angle)
     for i in (93, 95, 100):
