@@ -345,6 +345,37 @@ void om_collision(const om_model* m, om_data* d) {
       v3sub(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);
       if (v3dot(dif, dif) > bound * bound) continue;
     }
+    /* oriented-bounding-box rejection (6 face axes / lowest corner vs plane): conservative, so it
+     * never changes the contact set; it only keeps far-apart meshes out of the MPR query */
+    {
+      const double *ab2 = m->geom_aabb + 6 * g2, *R2 = d->geom_xmat + 9 * g2;
+      double c2w[3], dif[3];
+      mulmatvec3(c2w, R2, ab2);
+      v3sub(dif, d->geom_xpos + 3 * g2, d->geom_xpos + 3 * g1);
+      if (t1 == GEOM_PLANE) {
+        const double* pm = d->geom_xmat + 9 * g1;
+        double n[3] = {pm[2], pm[5], pm[8]};
+        double low = v3dot(dif, n) + v3dot(c2w, n);
+        for (int k = 0; k < 3; k++) low -= fabs(R2[k] * n[0] + R2[3 + k] * n[1] + R2[6 + k] * n[2]) * ab2[3 + k];
+        if (low > margin) continue;
+      } else {
+        const double *ab1 = m->geom_aabb + 6 * g1, *R1 = d->geom_xmat + 9 * g1;
+        double c1w[3], t[3];
+        int sep = 0;
+        mulmatvec3(c1w, R1, ab1);
+        for (int k = 0; k < 3; k++) t[k] = dif[k] + c2w[k] - c1w[k];
+        for (int i = 0; i < 3 && !sep; i++) {
+          double a1[3] = {R1[i], R1[3 + i], R1[6 + i]}, a2[3] = {R2[i], R2[3 + i], R2[6 + i]};
+          double r1 = ab1[3 + i] + margin, r2 = ab2[3 + i] + margin;
+          for (int k = 0; k < 3; k++) {
+            r1 += fabs(R2[k] * a1[0] + R2[3 + k] * a1[1] + R2[6 + k] * a1[2]) * ab2[3 + k];
+            r2 += fabs(R1[k] * a2[0] + R1[3 + k] * a2[1] + R1[6 + k] * a2[2]) * ab1[3 + k];
+          }
+          if (fabs(v3dot(t, a1)) > r1 || fabs(v3dot(t, a2)) > r2) sep = 1;
+        }
+        if (sep) continue;
+      }
+    }
     if (t1 == GEOM_PLANE) {
       if (t2 == GEOM_SPHERE) plane_sphere(m, d, p, g1, g2, margin);
       else if (t2 == GEOM_CYLINDER) plane_cylinder(m, d, p, g1, g2, margin);

@@ -64,25 +64,55 @@ static int build_layout(DevModel& m) {
   int nv = m.nv, nb = m.nbody;
   o.ldm = nv | 1;
   o.ldj = nv | 1;
+  // live for the whole step
   o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv); o.qacc = take(nv);
-  o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.xmat = take(nb * 9); o.xipos = take(nb * 3); o.ximat = take(nb * 9);
-  o.xanchor = take(m.njnt * 3); o.xaxis = take(m.njnt * 3);
-  o.rootcom = take(m.nroot * 3); o.cinert = take(nb * 10); o.crb = take(nb * 10); o.cdof = take(nv * 6);
-  o.cdofdot = take(nv * 6); o.cvel = take(nb * 6); o.cacc = take(nb * 6); o.cfrc = take(nb * 6);
-  o.M = take(nv * o.ldm); o.H = take(nv * o.ldm);
+  o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.cdof = take(nv * 6); o.cdofdot = take(nv * 6); o.cvel = take(nb * 6);
+  o.M = take(nv * o.ldm);
   o.qfrc_smooth = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
   o.actforce = take(m.nu); o.actlen = take(m.nu); o.actvel = take(m.nu);
-  o.gpos = take(m.ncgeom * 3);
   o.con = take(m.maxcon * CON_STRIDE);
-  o.J = take(m.maxcrow * o.ldj); o.tmpJ = take(6 * o.ldj);
   o.s_d1 = take(m.maxsimple); o.s_c1 = take(m.maxsimple); o.s_d2 = take(m.maxsimple); o.s_c2 = take(m.maxsimple);
-  o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxrow);
-  o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow); o.e_type = take(m.maxrow);
-  o.e_id = take(m.maxrow); o.e_state = take(m.maxrow);
+  o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxrow); o.e_info = take(m.maxrow);
+  o.J = take(m.maxcrow * o.ldj);
+  // region X (kinematics / dynamics scratch) and region Y (solver scratch) share the tail
+  int base = off;
+  o.xmat = take(nb * 9); o.cinert = take(nb * 10);
+  o.cacc = take(nb * 6); o.cfrc = take(nb * 6);
+  o.crb = o.cacc;                      // composite inertias (10/body) die before cacc/cfrc (6+6/body) are born
+  o.gpos = take(m.ncgeom * 3);
+  int endX = off;
+  off = base;
+  o.H = take(nv * o.ldm); o.tmpJ = take(6 * o.ldj);
+  o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
   o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
+  int endY = off;
+  off = std::max(endX, endY);
   o.total = off;
   return off;
 }
+
+// ----------------------------------------------------------------------------- model pack
+struct PackBuilder {
+  std::vector<uint32_t> w;
+  int addi(const std::vector<int>& v) {
+    int o = (int)w.size();
+    for (int x : v) w.push_back((uint32_t)x);
+    while (w.size() % 4) w.push_back(0);
+    return o;
+  }
+  int addu(const std::vector<uint32_t>& v) {
+    int o = (int)w.size();
+    for (uint32_t x : v) w.push_back(x);
+    while (w.size() % 4) w.push_back(0);
+    return o;
+  }
+  int addf(const std::vector<float>& v) {
+    int o = (int)w.size();
+    for (float x : v) { uint32_t u; memcpy(&u, &x, 4); w.push_back(u); }
+    while (w.size() % 4) w.push_back(0);
+    return o;
+  }
+};
 
 extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, ss_model** out) {
   if (!blob || !out) return ss_fail("ss_model_load_blob: null argument");
@@ -164,13 +194,14 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
                    gbody = i32(b, "geom_bodyid"), gdata = i32(b, "geom_dataid");
   std::vector<float> gsize = f32(b, "geom_size"), grb = f32(b, "geom_rbound"), gpos = f32(b, "geom_pos"), gquat = f32(b, "geom_quat");
   std::vector<int> cg_of(m.ngeom, -1), cg_geomid, cg_type, cg_body, cg_data, pc1, pc2;
-  std::vector<float> cg_size, cg_rb, cg_pos, cg_quat;
+  std::vector<float> cg_size, cg_rb, cg_pos, cg_quat, cg_aabb, gaabb = f32(b, "geom_aabb");
   auto cg = [&](int g) {
     if (cg_of[g] < 0) {
       cg_of[g] = (int)cg_geomid.size();
       cg_geomid.push_back(g); cg_type.push_back(gtype[g]); cg_body.push_back(gbody[g]); cg_data.push_back(gdata[g]);
       for (int k = 0; k < 3; k++) { cg_size.push_back(gsize[3 * g + k]); cg_pos.push_back(gpos[3 * g + k]); }
       for (int k = 0; k < 4; k++) cg_quat.push_back(gquat[4 * g + k]);
+      for (int k = 0; k < 6; k++) cg_aabb.push_back(gaabb[6 * g + k]);
       cg_rb.push_back(grb[g]);
     }
     return cg_of[g];
@@ -186,42 +217,68 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
   M->nrange = 0;
   for (int s : stype) if (s == SENS_RANGE) M->nrange++;
 
-#define UP(field, vec) m.field = upload(M, vec)
-  UP(body_parentid, parent); UP(body_rootidx, rootidx); UP(body_jntnum, i32(b, "body_jntnum")); UP(body_jntadr, i32(b, "body_jntadr"));
-  UP(body_dofnum, dofnum); UP(body_dofadr, dofadr); UP(lvl_adr, lvl_adr); UP(lvl_body, lvl_body); UP(child_adr, child_adr);
-  UP(child_list, child_list); UP(root_list, root_list); UP(body_dofmask, dofmask);
-  UP(body_pos, f32(b, "body_pos")); UP(body_quat, f32(b, "body_quat")); UP(body_ipos, f32(b, "body_ipos"));
-  UP(body_iquat, f32(b, "body_iquat")); UP(body_mass, f32(b, "body_mass")); UP(body_inertia, f32(b, "body_inertia"));
-  UP(body_gravcomp, gravcomp); UP(body_invweight0, f32(b, "body_invweight0")); UP(body_subtreemass, f32(b, "body_subtreemass"));
-  UP(jnt_type, jnt_type); UP(jnt_bodyid, i32(b, "jnt_bodyid")); UP(jnt_qposadr, jnt_qposadr); UP(jnt_dofadr, jnt_dofadr);
-  UP(jnt_limited, jnt_limited); UP(limited_list, limited_list);
-  UP(jnt_pos, f32(b, "jnt_pos")); UP(jnt_axis, f32(b, "jnt_axis")); UP(jnt_stiffness, f32(b, "jnt_stiffness"));
-  UP(jnt_range, f32(b, "jnt_range")); UP(jnt_margin, f32(b, "jnt_margin")); UP(jnt_solref, f32(b, "jnt_solref"));
-  UP(jnt_solimp, f32(b, "jnt_solimp")); UP(qpos_spring, f32(b, "qpos_spring"));
+  if (m.ncgeom > 65535) { delete M; return ss_fail("too many collision geoms"); }
+  std::vector<int> pair_cg(m.npair);
+  for (int p = 0; p < m.npair; p++) pair_cg[p] = pc1[p] | (pc2[p] << 16);
+  std::vector<float> pmargin = f32(b, "pair_margin");
+  m.max_margin = 0.f;
+  for (float x : pmargin) m.max_margin = std::max(m.max_margin, x);
+  PackBuilder P;
+  PackOffsets& k = m.pk;
+  k.body_parentid = P.addi(parent); k.body_rootidx = P.addi(rootidx); k.body_jntnum = P.addi(i32(b, "body_jntnum"));
+  k.body_jntadr = P.addi(i32(b, "body_jntadr")); k.body_dofnum = P.addi(dofnum); k.body_dofadr = P.addi(dofadr);
+  k.lvl_adr = P.addi(lvl_adr); k.lvl_body = P.addi(lvl_body); k.child_adr = P.addi(child_adr); k.child_list = P.addi(child_list);
+  k.root_list = P.addi(root_list); k.body_dofmask = P.addu(dofmask);
+  k.body_pos = P.addf(f32(b, "body_pos")); k.body_quat = P.addf(f32(b, "body_quat")); k.body_ipos = P.addf(f32(b, "body_ipos"));
+  k.body_iquat = P.addf(f32(b, "body_iquat")); k.body_mass = P.addf(f32(b, "body_mass")); k.body_inertia = P.addf(f32(b, "body_inertia"));
+  k.body_gravcomp = P.addf(gravcomp); k.body_invweight0 = P.addf(f32(b, "body_invweight0"));
+  k.jnt_type = P.addi(jnt_type); k.jnt_bodyid = P.addi(i32(b, "jnt_bodyid")); k.jnt_qposadr = P.addi(jnt_qposadr);
+  k.jnt_dofadr = P.addi(jnt_dofadr); k.limited_list = P.addi(limited_list);
+  k.jnt_pos = P.addf(f32(b, "jnt_pos")); k.jnt_axis = P.addf(f32(b, "jnt_axis")); k.jnt_stiffness = P.addf(f32(b, "jnt_stiffness"));
+  k.jnt_range = P.addf(f32(b, "jnt_range")); k.jnt_margin = P.addf(f32(b, "jnt_margin")); k.jnt_solref = P.addf(f32(b, "jnt_solref"));
+  k.jnt_solimp = P.addf(f32(b, "jnt_solimp"));
   M->qpos0_host = f32(b, "qpos0");
-  UP(qpos0, M->qpos0_host);
-  UP(dof_bodyid, i32(b, "dof_bodyid")); UP(dof_jntid, dof_jnt); UP(dof_parentid, dof_parent); UP(dof_qposadr, dof_qposadr);
-  UP(floss_list, floss_list);
-  UP(dof_armature, f32(b, "dof_armature")); UP(dof_damping, f32(b, "dof_damping")); UP(dof_frictionloss, floss);
-  UP(dof_invweight0, f32(b, "dof_invweight0")); UP(dof_solref, f32(b, "dof_solref")); UP(dof_solimp, f32(b, "dof_solimp"));
-  UP(cg_geomid, cg_geomid); UP(cg_type, cg_type); UP(cg_bodyid, cg_body); UP(cg_dataid, cg_data);
-  UP(cg_size, cg_size); UP(cg_rbound, cg_rb); UP(cg_pos, cg_pos); UP(cg_quat, cg_quat);
-  UP(pair_cg1, pc1); UP(pair_cg2, pc2); UP(pair_condim, i32(b, "pair_condim"));
-  UP(pair_friction, f32(b, "pair_friction")); UP(pair_solref, f32(b, "pair_solref")); UP(pair_solimp, f32(b, "pair_solimp"));
-  UP(pair_margin, f32(b, "pair_margin")); UP(pair_gap, f32(b, "pair_gap"));
-  UP(mesh_hulladr, i32(b, "mesh_hulladr")); UP(mesh_hullnum, i32(b, "mesh_hullnum")); UP(hull_vert, hull4);
-  UP(site_bodyid, i32(b, "site_bodyid")); UP(sensor_type, stype); UP(sensor_objid, i32(b, "sensor_objid"));
-  UP(sensor_adr, i32(b, "sensor_adr")); UP(site_pos, f32(b, "site_pos")); UP(site_quat, f32(b, "site_quat"));
-  UP(sensor_cutoff, f32(b, "sensor_cutoff"));
-  UP(eq_obj1id, i32(b, "eq_obj1id")); UP(eq_obj2id, i32(b, "eq_obj2id")); UP(eq_active0, i32(b, "eq_active0"));
-  UP(eq_data, f32(b, "eq_data")); UP(eq_solref, f32(b, "eq_solref")); UP(eq_solimp, f32(b, "eq_solimp"));
-  UP(actuator_ctrllimited, i32(b, "actuator_ctrllimited")); UP(actuator_forcelimited, i32(b, "actuator_forcelimited"));
-  UP(actuator_trntype, trntype); UP(actuator_trnid, trnid);
-  UP(actuator_gainprm, f32(b, "actuator_gainprm")); UP(actuator_biasprm, f32(b, "actuator_biasprm"));
-  UP(actuator_ctrlrange, f32(b, "actuator_ctrlrange")); UP(actuator_forcerange, f32(b, "actuator_forcerange"));
-  UP(act_moment, moment); UP(actuator_gear, gear);
-  UP(key_qpos, f32(b, "key_qpos")); UP(key_ctrl, f32(b, "key_ctrl"));
-#undef UP
+  k.qpos0 = P.addf(M->qpos0_host); k.qpos_spring = P.addf(f32(b, "qpos_spring"));
+  k.dof_bodyid = P.addi(i32(b, "dof_bodyid")); k.dof_jntid = P.addi(dof_jnt); k.dof_parentid = P.addi(dof_parent);
+  k.dof_qposadr = P.addi(dof_qposadr); k.floss_list = P.addi(floss_list);
+  k.dof_armature = P.addf(f32(b, "dof_armature")); k.dof_damping = P.addf(f32(b, "dof_damping")); k.dof_frictionloss = P.addf(floss);
+  k.dof_invweight0 = P.addf(f32(b, "dof_invweight0")); k.dof_solref = P.addf(f32(b, "dof_solref")); k.dof_solimp = P.addf(f32(b, "dof_solimp"));
+  k.cg_geomid = P.addi(cg_geomid); k.cg_type = P.addi(cg_type); k.cg_bodyid = P.addi(cg_body); k.cg_dataid = P.addi(cg_data);
+  k.cg_size = P.addf(cg_size); k.cg_rbound = P.addf(cg_rb); k.cg_pos = P.addf(cg_pos); k.cg_quat = P.addf(cg_quat); k.cg_aabb = P.addf(cg_aabb);
+  k.pair_cg = P.addi(pair_cg);
+  k.mesh_hulladr = P.addi(i32(b, "mesh_hulladr")); k.mesh_hullnum = P.addi(i32(b, "mesh_hullnum"));
+  // only the sites that sensors of the physics kernel use (IMU); lidar sites live in the ray model
+  {
+    std::vector<int> sobj = i32(b, "sensor_objid"), sadr = i32(b, "sensor_adr"), sbody = i32(b, "site_bodyid");
+    std::vector<float> spos = f32(b, "site_pos"), squat = f32(b, "site_quat");
+    std::vector<int> t2, o2, a2, sb2; std::vector<float> sp2, sq2;
+    for (size_t s = 0; s < stype.size(); s++) {
+      if (stype[s] == SENS_RANGE) continue;
+      int site = sobj[s];
+      t2.push_back(stype[s]); o2.push_back((int)sb2.size()); a2.push_back(sadr[s]);
+      sb2.push_back(sbody[site]);
+      for (int q = 0; q < 3; q++) sp2.push_back(spos[3 * site + q]);
+      for (int q = 0; q < 4; q++) sq2.push_back(squat[4 * site + q]);
+    }
+    m.nsensor = (int)t2.size();
+    k.sensor_type = P.addi(t2); k.sensor_objid = P.addi(o2); k.sensor_adr = P.addi(a2);
+    k.site_bodyid = P.addi(sb2); k.site_pos = P.addf(sp2); k.site_quat = P.addf(sq2);
+  }
+  k.eq_obj1id = P.addi(i32(b, "eq_obj1id")); k.eq_obj2id = P.addi(i32(b, "eq_obj2id")); k.eq_active0 = P.addi(i32(b, "eq_active0"));
+  k.eq_data = P.addf(f32(b, "eq_data")); k.eq_solref = P.addf(f32(b, "eq_solref")); k.eq_solimp = P.addf(f32(b, "eq_solimp"));
+  k.actuator_ctrllimited = P.addi(i32(b, "actuator_ctrllimited")); k.actuator_forcelimited = P.addi(i32(b, "actuator_forcelimited"));
+  k.actuator_gainprm = P.addf(f32(b, "actuator_gainprm")); k.actuator_biasprm = P.addf(f32(b, "actuator_biasprm"));
+  k.actuator_ctrlrange = P.addf(f32(b, "actuator_ctrlrange")); k.actuator_forcerange = P.addf(f32(b, "actuator_forcerange"));
+  k.act_moment = P.addf(moment);
+  k.nwords = (int)P.w.size();
+  M->pack_host = P.w;
+  m.pack = upload(M, P.w);
+  m.pair_condim = upload(M, i32(b, "pair_condim"));
+  m.pair_friction = upload(M, f32(b, "pair_friction")); m.pair_solref = upload(M, f32(b, "pair_solref"));
+  m.pair_solimp = upload(M, f32(b, "pair_solimp")); m.pair_margin = upload(M, pmargin); m.pair_gap = upload(M, f32(b, "pair_gap"));
+  m.hull_vert = upload(M, hull4);
+  m.key_qpos = upload(M, f32(b, "key_qpos")); m.key_ctrl = upload(M, f32(b, "key_ctrl"));
+  M->qpos0_dev = upload(M, M->qpos0_host);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ss_model_free(M); return ss_fail("model upload failed: %s", cudaGetErrorString(e)); }
   if (ss_rays_model_init(M) != 0) { ss_model_free(M); return -1; }
@@ -273,7 +330,8 @@ extern "C" int ss_model_set(ss_model* M, const char* field, const void* src, siz
   if (strcmp(field, "qpos0") == 0) {
     if (bytes != M->qpos0_host.size() * sizeof(double)) return ss_fail("ss_model_set(qpos0): expected %zu doubles", M->qpos0_host.size());
     for (size_t i = 0; i < M->qpos0_host.size(); i++) M->qpos0_host[i] = (float)((const double*)src)[i];
-    CUDA_OK(cudaMemcpy((void*)M->dm.qpos0, M->qpos0_host.data(), M->qpos0_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy((void*)(M->dm.pack + M->dm.pk.qpos0), M->qpos0_host.data(), M->qpos0_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy((void*)M->qpos0_dev, M->qpos0_host.data(), M->qpos0_host.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
   }
   if (strcmp(field, "opt_iterations") == 0 && bytes == sizeof(int)) { M->dm.iterations = *(const int*)src; return 0; }
@@ -291,10 +349,10 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   memset(&B->dbg, 0, sizeof(B->dbg));
   B->dm = M->dm;
   DevModel& m = B->dm;
-  m.maxcon = maxcon > 0 ? maxcon : 24;
+  m.maxcon = maxcon > 0 ? maxcon : 16;
   int nsimple = m.neq + m.nfloss + 2 * m.nlimited;
   m.maxsimple = nsimple;
-  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 96;
+  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 64;
   m.maxrow = m.maxsimple + m.maxcrow;
   int floats = build_layout(m);
   B->smem_per_env = (size_t)floats * sizeof(float);
@@ -302,12 +360,17 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   int max_smem = 0, sms = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
-  int wpb = (int)(max_smem / B->smem_per_env);
-  if (wpb < 1) { delete B; return ss_fail("env working set (%zu B) exceeds shared memory (%d B)", B->smem_per_env, max_smem); }
-  wpb = std::min(wpb, 8);
+  size_t pack_bytes = (size_t)m.pk.nwords * 4 + 2048;  // + static shared (mbarrier, compiler scratch) slack
+  int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
+  if (wpb < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
+  wpb = std::min(wpb, 16);
+  if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs
+  B->sync_level = 1;
+  if (const char* e = getenv("SS_SYNC")) B->sync_level = atoi(e);
+  B->pack_bytes = (size_t)m.pk.nwords * 4;
   B->warps_per_block = wpb;
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
-  cudaError_t e = cudaFuncSetAttribute(ss_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * B->smem_per_env));
+  cudaError_t e = cudaFuncSetAttribute(ss_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B->pack_bytes + wpb * B->smem_per_env));
   if (e != cudaSuccess) { delete B; return ss_fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   *out = B;
   return 0;
@@ -330,7 +393,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   StepArgs a;
   memset(&a, 0, sizeof(a));
   const ss_buffers& f = B->bufs;
-  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only;
+  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level;
   a.qpos = f.qpos; a.qvel = f.qvel; a.warm = f.qacc_warmstart; a.time = f.time; a.ctrl = f.ctrl;
   a.xpos = f.xpos; a.xquat = f.xquat; a.act_length = f.act_length; a.act_velocity = f.act_velocity;
   a.sensordata = f.sensordata; a.qacc = f.qacc; a.ncon = f.ncon; a.contact_geom = f.contact_geom;
@@ -341,7 +404,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   cudaSetDevice(B->model->device);
   B->dm.iterations = B->model->dm.iterations;  // runtime-settable solver options (ss_model_set)
   B->dm.tolerance = B->model->dm.tolerance;
-  size_t smem = B->warps_per_block * B->smem_per_env;
+  size_t smem = B->pack_bytes + B->warps_per_block * B->smem_per_env;
   ss_physics_kernel<<<B->grid, B->warps_per_block * 32, smem, (cudaStream_t)stream>>>(B->dm, a);
   B->launches++;
   CUDA_OK(cudaGetLastError());

@@ -18,6 +18,8 @@ struct ss_model {
   DevModel dm;
   RayModel rm;
   std::vector<float> qpos0_host, cam_fovy_host;
+  std::vector<uint32_t> pack_host;
+  const float* qpos0_dev = nullptr;
   std::vector<void*> dev_allocs;
 };
 
@@ -27,8 +29,8 @@ struct ss_batch {
   ss_buffers bufs;
   ss_debug_buffers dbg;
   DevModel dm;  // model + this batch's buffer sizes and shared-memory layout
-  size_t smem_per_env;
-  int warps_per_block, grid;
+  size_t smem_per_env, pack_bytes;
+  int warps_per_block, grid, sync_level;
   long launches;
   float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
 };

@@ -39,7 +39,7 @@ extern "C" int ss_batch_reset(ss_batch* B, const int32_t* mask, int key_id, ss_s
   const DevModel& m = B->dm;
   if (key_id >= m.nkey) return ss_fail("ss_batch_reset: keyframe %d out of range", key_id);
   cudaSetDevice(B->model->device);
-  const float* qsrc = key_id < 0 ? B->model->dm.qpos0 : m.key_qpos + (size_t)key_id * m.nq;
+  const float* qsrc = key_id < 0 ? B->model->qpos0_dev : m.key_qpos + (size_t)key_id * m.nq;
   const float* csrc = key_id < 0 ? nullptr : m.key_ctrl + (size_t)key_id * m.nu;
   reset_kernel<<<(B->nenv + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B->nenv, m.nq, m.nv, m.nu, qsrc, csrc, mask,
                                                                           B->bufs.qpos, B->bufs.qvel, B->bufs.qacc_warmstart,

@@ -5,10 +5,15 @@
 // persistent sm_100a kernel: one warp owns one env, the env's whole working set lives in that
 // warp's slice of shared memory for all nsteps, and HBM is touched only to load the state and
 // ctrl at the start and to store state + observations at the end (828 B/env-step algorithmic).
+// The model's small tables are pulled into shared memory once per CTA by a TMA bulk copy.
 //
 // Lane mapping: lane = dof for joint-space vectors and matrix rows, lane = body inside one tree
 // level for the kinematic passes, lane = constraint row / contact for the solver's row passes.
 // Cross-lane traffic goes through shared memory + __syncwarp or through shuffles for reductions.
+//
+// Code-size discipline (the first profile was instruction-fetch bound): every model-dependent
+// stage has exactly one call site and is inlined so that DevModel fields stay constant-bank
+// operands; the generic dense-algebra / row-pass helpers are __noinline__ single copies.
 #include "model.cuh"
 #include "batch.cuh"
 #include <math_constants.h>
@@ -18,6 +23,10 @@
 #define MAXVAL 1e10f
 #define MINIMP 0.0001f
 #define MAXIMP 0.9999f
+
+extern __shared__ __align__(16) float smem[];  // [model pack | env slice 0 | env slice 1 | ...]
+#define PKF(name) (smem + m.pk.name)
+#define PKI(name) (reinterpret_cast<const int*>(smem) + m.pk.name)
 
 // ----------------------------------------------------------------------------- small math
 __device__ __forceinline__ float warp_sum(float v) {
@@ -57,11 +66,6 @@ __device__ __forceinline__ void matT_vec(float* r, const float* M, const float* 
         z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
   r[0] = x; r[1] = y; r[2] = z;
 }
-__device__ __forceinline__ void quat_rot(float* r, const float* q, const float* v) {
-  float R[9];
-  quat2mat(R, q);
-  mat_vec(r, R, v);
-}
 __device__ __forceinline__ void mul_inert_vec(float* r, const float* i, const float* v) {
   r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
   r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
@@ -84,10 +88,17 @@ __device__ __forceinline__ void cross_force(float* r, const float* vel, const fl
   r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
   cross3(r + 3, vel, f + 3);
 }
+__device__ __forceinline__ void normalize3(float* a) {
+  float n = sqrtf(dot3(a, a));
+  if (n < 1e-20f) { a[0] = 1; a[1] = a[2] = 0; return; }
+  float inv = 1.0f / n;
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+}
 
-// in-place Cholesky of the dense n x n matrix A (row stride ld) held in shared memory.
+// ----------------------------------------------------------------------------- dense algebra (single copies)
+// in-place Cholesky of the dense n x n matrix A (row stride ld, lower triangle) in shared memory.
 // Lane i owns row i (+32 for n > 32); left-looking so that only finished columns are read.
-__device__ void chol_factor(float* A, int n, int ld, int lane) {
+__device__ __noinline__ void chol_factor(float* A, int n, int ld, int lane) {
   for (int j = 0; j < n; j++) {
     float s[2] = {0, 0};
 #pragma unroll
@@ -114,7 +125,7 @@ __device__ void chol_factor(float* A, int n, int ld, int lane) {
 }
 
 // solve L L^T x = b in place; x is a shared-memory vector of length n
-__device__ void chol_solve(const float* L, float* x, int n, int ld, int lane) {
+__device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld, int lane) {
   for (int j = 0; j < n; j++) {
     float xj = x[j] / L[j * ld + j];
     __syncwarp();
@@ -136,65 +147,287 @@ __device__ void chol_solve(const float* L, float* x, int n, int ld, int lane) {
 }
 
 // y = A x for the symmetric dense matrix in shared memory (full storage)
-__device__ __forceinline__ void symv(float* y, const float* A, const float* x, int n, int ld, int lane) {
+__device__ __noinline__ void symv(float* y, const float* A, const float* x, int n, int ld, int lane) {
   for (int i = lane; i < n; i += 32) {
     float s = 0;
     const float* r = A + i * ld;
     for (int k = 0; k < n; k++) s += r[k] * x[k];
     y[i] = s;
   }
+  __syncwarp();
 }
 
-// ----------------------------------------------------------------------------- S1: position
-__device__ void kinematics(const DevModel& m, float* S, int lane) {
+// copy the lower triangle of src into dst (row stride ld)
+__device__ __noinline__ void copy_lower(float* dst, const float* src, int n, int ld, int lane) {
+  for (int i = lane; i < n; i += 32)
+    for (int k = 0; k <= i; k++) dst[i * ld + k] = src[i * ld + k];
+  __syncwarp();
+}
+
+// ----------------------------------------------------------------------------- constraint rows (single copies)
+struct Rows {
+  const int *sd1, *sd2;
+  int* info;                       // type | state << 4 | id << 8
+  const float *sc1, *sc2, *J, *eD, *eR, *efl, *con;
+  float *jar, *jv, *force;
+  int ns, nefc, ncon, ldj, nv;
+};
+#define INFO_TYPE(x) ((x) & 15)
+#define INFO_STATE(x) (((x) >> 4) & 15)
+#define INFO_ID(x) ((x) >> 8)
+
+// Row-parallel evaluation of the constraint cost at jar (+ alpha*jv).
+// WRITE=true : alpha ignored; writes force/state, returns cost in c_out.
+// WRITE=false: line-search probe; returns cost, derivative g, curvature h (constraint part only).
+template <bool WRITE>
+__device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& c_out, float& g_out, float& h_out, int lane) {
+  const float *jar = R.jar, *jv = R.jv, *eD = R.eD, *eR = R.eR, *efl = R.efl;
+  float c = 0, g = 0, h = 0;
+  for (int r = lane; r < R.nefc; r += 32) {
+    int inf = R.info[r], tp = INFO_TYPE(inf);
+    if (tp == CNSTR_CONTACT_ELLIPTIC) continue;
+    float D = eD[r], v = WRITE ? 0.f : jv[r], x = WRITE ? jar[r] : jar[r] + alpha * v;
+    float f = 0; int st = ST_SATISFIED;
+    if (tp == CNSTR_EQUALITY) {
+      c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC;
+    } else if (tp == CNSTR_FRICTION) {
+      float fl = efl[r], Rr = eR[r];
+      if (x <= -Rr * fl) { c += -0.5f * Rr * fl * fl - fl * x; g += -fl * v; f = fl; st = ST_LINEARNEG; }
+      else if (x >= Rr * fl) { c += -0.5f * Rr * fl * fl + fl * x; g += fl * v; f = -fl; st = ST_LINEARPOS; }
+      else { c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC; }
+    } else {  // limit or frictionless contact
+      if (x < 0) { c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC; }
+    }
+    if (WRITE) { R.force[r] = f; R.info[r] = (inf & ~0xF0) | (st << 4); }
+  }
+  for (int k = lane; k < R.ncon; k += 32) {
+    const float* con = R.con + k * CON_STRIDE;
+    int dim = __float_as_int(con[C_DIM]);
+    if (dim == 1) continue;
+    int i = __float_as_int(con[C_EFC]);
+    if (i < 0) continue;
+    float mu = con[C_MU];
+    float x0 = WRITE ? jar[i] : jar[i] + alpha * jv[i];
+    float N = x0 * mu, N1 = WRITE ? 0.f : jv[i] * mu, TT = 0, UV = 0, VV = 0;
+    for (int j = 1; j < dim; j++) {
+      float fj = con[C_FRICTION + j - 1];
+      float v = WRITE ? 0.f : jv[i + j] * fj, u = (WRITE ? jar[i + j] : jar[i + j] + alpha * jv[i + j]) * fj;
+      TT += u * u; UV += u * v; VV += v * v;
+    }
+    float T = sqrtf(TT);
+    int st;
+    if (N >= mu * T || (T <= 0 && N >= 0)) {
+      st = ST_SATISFIED;
+      if (WRITE) for (int j = 0; j < dim; j++) R.force[i + j] = 0;
+    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      st = ST_QUADRATIC;
+      for (int j = 0; j < dim; j++) {
+        float D = eD[i + j], v = WRITE ? 0.f : jv[i + j], x = WRITE ? jar[i + j] : jar[i + j] + alpha * v;
+        c += 0.5f * D * x * x; g += D * x * v; h += D * v * v;
+        if (WRITE) R.force[i + j] = -D * x;
+      }
+    } else {
+      st = ST_CONE;
+      float Dm = eD[i] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
+      float NT = N - mu * T;
+      c += 0.5f * Dm * NT * NT;
+      if (WRITE) {
+        float f0 = -Dm * NT * mu;
+        R.force[i] = f0;
+        for (int j = 1; j < dim; j++) {
+          float fj = con[C_FRICTION + j - 1];
+          R.force[i + j] = -f0 / T * (jar[i + j] * fj) * fj;
+        }
+      } else {
+        float T1 = UV / T, T2d = (VV - T1 * T1) / T, NT1 = N1 - mu * T1;
+        g += Dm * NT * NT1; h += Dm * (NT1 * NT1 - NT * mu * T2d);
+      }
+    }
+    if (WRITE) for (int j = 0; j < dim; j++) R.info[i + j] = (R.info[i + j] & ~0xF0) | (st << 4);
+  }
+  c_out = warp_sum(c);
+  if (!WRITE) { g_out = warp_sum(g); h_out = warp_sum(h); }
+  if (WRITE) __syncwarp();
+}
+
+// y[r] = J[r,:] . x for all rows (simple rows + dense contact rows)
+__device__ __noinline__ void mul_J(const Rows R, float* y, const float* x, int lane) {
+  for (int r = lane; r < R.nefc; r += 32) {
+    float s;
+    if (r < R.ns) {
+      s = R.sc1[r] * x[R.sd1[r]];
+      int d2 = R.sd2[r];
+      if (d2 >= 0) s += R.sc2[r] * x[d2];
+    } else {
+      const float* Jr = R.J + (r - R.ns) * R.ldj;
+      s = 0;
+      for (int k = 0; k < R.nv; k++) s += Jr[k] * x[k];
+    }
+    y[r] = s;
+  }
+  __syncwarp();
+}
+
+// y[i] = sum_r J[r,i] f[r]
+__device__ __noinline__ void mul_JT(const Rows R, float* y, const float* f, int lane) {
+  for (int i = lane; i < R.nv; i += 32) {
+    float s = 0;
+    for (int r = 0; r < R.ns; r++) {
+      if (R.sd1[r] == i) s += R.sc1[r] * f[r];
+      if (R.sd2[r] == i) s += R.sc2[r] * f[r];
+    }
+    const float* Jc = R.J + i;
+    for (int r = R.ns; r < R.nefc; r++) s += Jc[(r - R.ns) * R.ldj] * f[r];
+    y[i] = s;
+  }
+  __syncwarp();
+}
+
+// H = M + J^T D J over quadratic rows + elliptic cone blocks (lane i owns row i of the lower
+// triangle), then Cholesky-factored in place.
+__device__ __noinline__ void build_hessian(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane) {
+  int nv = R.nv, ldj = R.ldj, ns = R.ns;
+  for (int i = lane; i < nv; i += 32) {
+    float* Hi = H + i * ld;
+    const float* Mi = M + i * ld;
+    for (int k = 0; k <= i; k++) Hi[k] = Mi[k];
+    for (int r = 0; r < ns; r++) {
+      if (INFO_STATE(R.info[r]) != ST_QUADRATIC) continue;
+      int d1 = R.sd1[r], d2 = R.sd2[r];
+      float D = R.eD[r], c1 = R.sc1[r], c2 = R.sc2[r];
+      if (d1 == i) Hi[i] += D * c1 * c1;
+      if (d2 == i) Hi[i] += D * c2 * c2;
+      if (d2 >= 0) {
+        int hi = max(d1, d2), lo = min(d1, d2);
+        if (hi == i) Hi[lo] += D * c1 * c2;
+      }
+    }
+  }
+  for (int r = ns; r < R.nefc; r++) {
+    int inf = R.info[r], st = INFO_STATE(inf);
+    if (st == ST_QUADRATIC) {
+      const float* Jr = R.J + (r - ns) * ldj;
+      float D = R.eD[r];
+      for (int i = lane; i < nv; i += 32) {
+        float s = D * Jr[i];
+        if (s != 0) {
+          float* Hi = H + i * ld;
+          for (int k = 0; k <= i; k++) Hi[k] += s * Jr[k];
+        }
+      }
+    } else if (st == ST_CONE) {
+      const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+      int dim = __float_as_int(con[C_DIM]);
+      float mu = con[C_MU], U[6], sc[6], T2 = 0, Hc[36];
+      sc[0] = mu; U[0] = R.jar[r] * mu;
+      for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = R.jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
+      float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
+      float iT = 1.0f / T;
+      Hc[0] = Dm;
+      for (int j = 1; j < dim; j++) Hc[j] = Hc[j * dim] = -Dm * mu * U[j] * iT;
+      for (int j = 1; j < dim; j++)
+        for (int k = 1; k < dim; k++)
+          Hc[j * dim + k] = Dm * (mu * N * U[j] * U[k] * iT * iT * iT - (j == k ? mu * (N - mu * T) * iT : 0.f));
+      for (int j = 0; j < dim; j++) for (int k = 0; k < dim; k++) Hc[j * dim + k] *= sc[j] * sc[k];
+      const float* Jc = R.J + (r - ns) * ldj;
+      __syncwarp();
+      for (int i = lane; i < nv; i += 32)
+        for (int j = 0; j < dim; j++) {
+          float t = 0;
+          for (int k = 0; k < dim; k++) t += Hc[j * dim + k] * Jc[k * ldj + i];
+          tmpJ[j * ldj + i] = t;
+        }
+      __syncwarp();
+      for (int i = lane; i < nv; i += 32) {
+        float* Hi = H + i * ld;
+        for (int j = 0; j < dim; j++) {
+          float s = Jc[j * ldj + i];
+          if (s != 0) {
+            const float* tj = tmpJ + j * ldj;
+            for (int k = 0; k <= i; k++) Hi[k] += s * tj[k];
+          }
+        }
+      }
+      r += dim - 1;
+    }
+  }
+  __syncwarp();
+  chol_factor(H, nv, ld, lane);
+}
+
+// ----------------------------------------------------------------------------- S1: kinematics + inertias + dof axes
+// One pass over the tree levels: body frames, spatial inertia about the tree's reference point
+// (the root body's origin) and the motion axis of every dof [upstream mj_kinematics + mj_comPos;
+// MuJoCo uses the subtree COM as reference point, any common point gives the same dynamics].
+__device__ __forceinline__ void kinematics(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
-  float *xpos = S + o.xpos, *xquat = S + o.xquat, *xmat = S + o.xmat, *xipos = S + o.xipos, *ximat = S + o.ximat;
+  float *xpos = S + o.xpos, *xquat = S + o.xquat, *xmat = S + o.xmat, *cinert = S + o.cinert, *cdof = S + o.cdof;
   const float* qpos = S + o.qpos;
   if (lane == 0) {
     xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
-    xipos[0] = xipos[1] = xipos[2] = 0;
-    for (int k = 0; k < 9; k++) { xmat[k] = (k % 4 == 0) ? 1.f : 0.f; ximat[k] = xmat[k]; }
+    for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
+    for (int k = 0; k < 10; k++) cinert[k] = 0;
   }
   __syncwarp();
   for (int lv = 0; lv < m.nlevel; lv++) {
-    for (int idx = m.lvl_adr[lv] + lane; idx < m.lvl_adr[lv + 1]; idx += 32) {
-      int b = m.lvl_body[idx], p = m.body_parentid[b], jn = m.body_jntnum[b], ja = m.body_jntadr[b];
-      float pos[3], q[4];
-      if (jn == 1 && m.jnt_type[ja] == JNT_FREE) {
-        int qa = m.jnt_qposadr[ja];
+    for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
+      int b = PKI(lvl_body)[idx], p = PKI(body_parentid)[b], jn = PKI(body_jntnum)[b], ja = PKI(body_jntadr)[b];
+      int rb = PKI(root_list)[PKI(body_rootidx)[b]];
+      float pos[3], q[4], ref[3];
+      bool isfree = (jn == 1 && PKI(jnt_type)[ja] == JNT_FREE);
+      if (isfree) {
+        int qa = PKI(jnt_qposadr)[ja];
         pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
         q[0] = qpos[qa + 3]; q[1] = qpos[qa + 4]; q[2] = qpos[qa + 5]; q[3] = qpos[qa + 6];
         quat_normalize(q);
-        float* an = S + o.xanchor + 3 * ja; float* ax = S + o.xaxis + 3 * ja;
-        an[0] = pos[0]; an[1] = pos[1]; an[2] = pos[2]; ax[0] = 0; ax[1] = 0; ax[2] = 1;
       } else {
-        float t[3], bq[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
-        float bp[3] = {m.body_pos[3 * b], m.body_pos[3 * b + 1], m.body_pos[3 * b + 2]};
+        const float *bq = PKF(body_quat) + 4 * b, *bp = PKF(body_pos) + 3 * b;
+        float t[3];
         mat_vec(t, xmat + 9 * p, bp);
         pos[0] = xpos[3 * p] + t[0]; pos[1] = xpos[3 * p + 1] + t[1]; pos[2] = xpos[3 * p + 2] + t[2];
         quat_mul(q, xquat + 4 * p, bq);
+      }
+      if (lv == 0) { ref[0] = pos[0]; ref[1] = pos[1]; ref[2] = pos[2]; }
+      else { ref[0] = xpos[3 * rb]; ref[1] = xpos[3 * rb + 1]; ref[2] = xpos[3 * rb + 2]; }
+      if (isfree) {
+        int da = PKI(jnt_dofadr)[ja];
+        float R[9];
+        quat2mat(R, q);
+        float off[3] = {ref[0] - pos[0], ref[1] - pos[1], ref[2] - pos[2]};
+        for (int k = 0; k < 3; k++) {
+          float* c = cdof + 6 * (da + k);
+          c[0] = c[1] = c[2] = 0; c[3] = (k == 0); c[4] = (k == 1); c[5] = (k == 2);
+          float a3[3] = {R[k], R[3 + k], R[6 + k]};
+          float* cr = cdof + 6 * (da + 3 + k);
+          cr[0] = a3[0]; cr[1] = a3[1]; cr[2] = a3[2];
+          cross3(cr + 3, a3, off);
+        }
+      } else {
         for (int j = ja; j < ja + jn; j++) {
-          float jp[3] = {m.jnt_pos[3 * j], m.jnt_pos[3 * j + 1], m.jnt_pos[3 * j + 2]};
-          float jax[3] = {m.jnt_axis[3 * j], m.jnt_axis[3 * j + 1], m.jnt_axis[3 * j + 2]};
+          const float *jp = PKF(jnt_pos) + 3 * j, *jax = PKF(jnt_axis) + 3 * j;
           float R[9], anchor[3], axis[3], r[3];
           quat2mat(R, q);
           mat_vec(r, R, jp); anchor[0] = pos[0] + r[0]; anchor[1] = pos[1] + r[1]; anchor[2] = pos[2] + r[2];
           mat_vec(axis, R, jax);
-          int qa = m.jnt_qposadr[j];
-          float dq = qpos[qa] - m.qpos0[qa];
-          if (m.jnt_type[j] == JNT_SLIDE) {
+          int qa = PKI(jnt_qposadr)[j];
+          float dq = qpos[qa] - PKF(qpos0)[qa];
+          float* c = cdof + 6 * PKI(jnt_dofadr)[j];
+          if (PKI(jnt_type)[j] == JNT_SLIDE) {
             pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+            c[0] = c[1] = c[2] = 0; c[3] = axis[0]; c[4] = axis[1]; c[5] = axis[2];
           } else {
             float sn, cs;
             sincosf(0.5f * dq, &sn, &cs);
             float qr[4] = {cs, jax[0] * sn, jax[1] * sn, jax[2] * sn}, qn[4];
             quat_mul(qn, q, qr);
             q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
-            quat_rot(r, q, jp);
+            quat2mat(R, q);
+            mat_vec(r, R, jp);
             pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+            float off[3] = {ref[0] - anchor[0], ref[1] - anchor[1], ref[2] - anchor[2]};
+            c[0] = axis[0]; c[1] = axis[1]; c[2] = axis[2];
+            cross3(c + 3, axis, off);
           }
-          float* an = S + o.xanchor + 3 * j; float* ax = S + o.xaxis + 3 * j;
-          an[0] = anchor[0]; an[1] = anchor[1]; an[2] = anchor[2]; ax[0] = axis[0]; ax[1] = axis[1]; ax[2] = axis[2];
         }
         quat_normalize(q);
       }
@@ -204,93 +437,43 @@ __device__ void kinematics(const DevModel& m, float* S, int lane) {
       quat2mat(R, q);
 #pragma unroll
       for (int k = 0; k < 9; k++) xmat[9 * b + k] = R[k];
-      float ip[3] = {m.body_ipos[3 * b], m.body_ipos[3 * b + 1], m.body_ipos[3 * b + 2]};
-      float iq[4] = {m.body_iquat[4 * b], m.body_iquat[4 * b + 1], m.body_iquat[4 * b + 2], m.body_iquat[4 * b + 3]};
-      mat_vec(t, R, ip);
-      xipos[3 * b] = pos[0] + t[0]; xipos[3 * b + 1] = pos[1] + t[1]; xipos[3 * b + 2] = pos[2] + t[2];
-      quat_mul(qi, q, iq);
+      // spatial inertia about the reference point, world axes
+      mat_vec(t, R, PKF(body_ipos) + 3 * b);
+      float off[3] = {pos[0] + t[0] - ref[0], pos[1] + t[1] - ref[1], pos[2] + t[2] - ref[2]};
+      quat_mul(qi, q, PKF(body_iquat) + 4 * b);
       quat2mat(R, qi);
-#pragma unroll
-      for (int k = 0; k < 9; k++) ximat[9 * b + k] = R[k];
+      float I0 = PKF(body_inertia)[3 * b], I1 = PKF(body_inertia)[3 * b + 1], I2 = PKF(body_inertia)[3 * b + 2];
+      float mass = PKF(body_mass)[b], o2 = dot3(off, off);
+      float* ci = cinert + 10 * b;
+#define IW(r, c) (R[3 * r] * I0 * R[3 * c] + R[3 * r + 1] * I1 * R[3 * c + 1] + R[3 * r + 2] * I2 * R[3 * c + 2])
+      ci[0] = IW(0, 0) + mass * (o2 - off[0] * off[0]);
+      ci[1] = IW(1, 1) + mass * (o2 - off[1] * off[1]);
+      ci[2] = IW(2, 2) + mass * (o2 - off[2] * off[2]);
+      ci[3] = IW(0, 1) - mass * off[0] * off[1];
+      ci[4] = IW(0, 2) - mass * off[0] * off[2];
+      ci[5] = IW(1, 2) - mass * off[1] * off[2];
+#undef IW
+      ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2]; ci[9] = mass;
     }
     __syncwarp();
   }
 }
 
-// tree COM, spatial inertias, dof axes, composite inertia, joint-space inertia M
-__device__ void com_crb(const DevModel& m, float* S, int lane) {
+// composite inertia (children gathered level by level) and the dense joint-space inertia M
+__device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
-  const float *xipos = S + o.xipos, *ximat = S + o.ximat, *xmat = S + o.xmat;
-  float *rootcom = S + o.rootcom, *cinert = S + o.cinert, *crb = S + o.crb, *cdof = S + o.cdof, *M = S + o.M;
-  int nb = m.nbody, nv = m.nv;
-  for (int r = 0; r < m.nroot; r++) {
-    float sx = 0, sy = 0, sz = 0;
-    for (int b = 1 + lane; b < nb; b += 32)
-      if (m.body_rootidx[b] == r) {
-        float ms = m.body_mass[b];
-        sx += ms * xipos[3 * b]; sy += ms * xipos[3 * b + 1]; sz += ms * xipos[3 * b + 2];
-      }
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    int rb = m.root_list[r];
-    float tm = m.body_subtreemass[rb];
-    if (lane == 0) {
-      if (tm < MINVAL) { rootcom[3 * r] = xipos[3 * rb]; rootcom[3 * r + 1] = xipos[3 * rb + 1]; rootcom[3 * r + 2] = xipos[3 * rb + 2]; }
-      else { float inv = 1.0f / tm; rootcom[3 * r] = sx * inv; rootcom[3 * r + 1] = sy * inv; rootcom[3 * r + 2] = sz * inv; }
-    }
-  }
-  __syncwarp();
-  for (int b = lane; b < nb; b += 32) {
-    float* ci = cinert + 10 * b;
-    if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
-    const float *R = ximat + 9 * b, *com = rootcom + 3 * m.body_rootidx[b];
-    float I0 = m.body_inertia[3 * b], I1 = m.body_inertia[3 * b + 1], I2 = m.body_inertia[3 * b + 2], mass = m.body_mass[b];
-    float off[3] = {xipos[3 * b] - com[0], xipos[3 * b + 1] - com[1], xipos[3 * b + 2] - com[2]};
-    float o2 = dot3(off, off);
-#define IW(r, c) (R[3 * r] * I0 * R[3 * c] + R[3 * r + 1] * I1 * R[3 * c + 1] + R[3 * r + 2] * I2 * R[3 * c + 2])
-    ci[0] = IW(0, 0) + mass * (o2 - off[0] * off[0]);
-    ci[1] = IW(1, 1) + mass * (o2 - off[1] * off[1]);
-    ci[2] = IW(2, 2) + mass * (o2 - off[2] * off[2]);
-    ci[3] = IW(0, 1) - mass * off[0] * off[1];
-    ci[4] = IW(0, 2) - mass * off[0] * off[2];
-    ci[5] = IW(1, 2) - mass * off[1] * off[2];
-#undef IW
-    ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2]; ci[9] = mass;
-  }
-  for (int j = lane; j < m.njnt; j += 32) {
-    int b = m.jnt_bodyid[j], da = m.jnt_dofadr[j];
-    const float *com = rootcom + 3 * m.body_rootidx[b], *an = S + o.xanchor + 3 * j, *ax = S + o.xaxis + 3 * j;
-    float off[3] = {com[0] - an[0], com[1] - an[1], com[2] - an[2]};
-    int t = m.jnt_type[j];
-    if (t == JNT_FREE) {
-      for (int k = 0; k < 3; k++) {
-        float* c = cdof + 6 * (da + k);
-        c[0] = c[1] = c[2] = 0; c[3] = (k == 0); c[4] = (k == 1); c[5] = (k == 2);
-        float a3[3] = {xmat[9 * b + k], xmat[9 * b + 3 + k], xmat[9 * b + 6 + k]};
-        float* cr = cdof + 6 * (da + 3 + k);
-        cr[0] = a3[0]; cr[1] = a3[1]; cr[2] = a3[2];
-        cross3(cr + 3, a3, off);
-      }
-    } else if (t == JNT_SLIDE) {
-      float* c = cdof + 6 * da;
-      c[0] = c[1] = c[2] = 0; c[3] = ax[0]; c[4] = ax[1]; c[5] = ax[2];
-    } else {
-      float* c = cdof + 6 * da;
-      float a3[3] = {ax[0], ax[1], ax[2]};
-      c[0] = a3[0]; c[1] = a3[1]; c[2] = a3[2];
-      cross3(c + 3, a3, off);
-    }
-  }
+  const float *cinert = S + o.cinert, *cdof = S + o.cdof;
+  float *crb = S + o.crb, *M = S + o.M;
+  int nv = m.nv;
   for (int k = lane; k < nv * o.ldm; k += 32) M[k] = 0;
-  __syncwarp();
-  // composite inertia: every body gathers its finished children, deepest level first
   for (int lv = m.nlevel - 1; lv >= 0; lv--) {
-    for (int idx = m.lvl_adr[lv] + lane; idx < m.lvl_adr[lv + 1]; idx += 32) {
-      int b = m.lvl_body[idx];
+    for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
+      int b = PKI(lvl_body)[idx];
       float acc[10];
 #pragma unroll
       for (int k = 0; k < 10; k++) acc[k] = cinert[10 * b + k];
-      for (int c = m.child_adr[b]; c < m.child_adr[b + 1]; c++) {
-        const float* cc = crb + 10 * m.child_list[c];
+      for (int c = PKI(child_adr)[b]; c < PKI(child_adr)[b + 1]; c++) {
+        const float* cc = crb + 10 * PKI(child_list)[c];
 #pragma unroll
         for (int k = 0; k < 10; k++) acc[k] += cc[k];
       }
@@ -301,11 +484,11 @@ __device__ void com_crb(const DevModel& m, float* S, int lane) {
   }
   for (int i = lane; i < nv; i += 32) {
     float buf[6];
-    mul_inert_vec(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
-    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+    mul_inert_vec(buf, crb + 10 * PKI(dof_bodyid)[i], cdof + 6 * i);
+    for (int j = i; j >= 0; j = PKI(dof_parentid)[j]) {
       const float* c = cdof + 6 * j;
       float v = c[0] * buf[0] + c[1] * buf[1] + c[2] * buf[2] + c[3] * buf[3] + c[4] * buf[4] + c[5] * buf[5];
-      if (j == i) v += m.dof_armature[i];
+      if (j == i) v += PKF(dof_armature)[i];
       M[i * o.ldm + j] = v;
       M[j * o.ldm + i] = v;
     }
@@ -320,7 +503,7 @@ struct Cvx {
   const float4* verts;
 };
 
-__device__ void support(const Cvx& g, const float* dir, float* out, int lane) {
+__device__ __noinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
   float l[3], r[3] = {0, 0, 0};
   matT_vec(l, g.mat, dir);
   if (g.type == GEOM_SPHERE) {
@@ -335,6 +518,7 @@ __device__ void support(const Cvx& g, const float* dir, float* out, int lane) {
     r[2] = l[2] > 0 ? g.size[1] : -g.size[1];
   } else if (g.type == GEOM_MESH) {
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
+#pragma unroll 4
     for (int i = lane; i < g.nvert; i += 32) {
       float4 v = __ldg(g.verts + i);
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
@@ -354,7 +538,7 @@ __device__ void support(const Cvx& g, const float* dir, float* out, int lane) {
 
 struct Spt { float v[3], v1[3], v2[3]; };
 
-__device__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
+__device__ __noinline__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
   float nd[3] = {-dir[0], -dir[1], -dir[2]};
   support(a, dir, s.v1, lane);
   support(b, nd, s.v2, lane);
@@ -365,12 +549,6 @@ __device__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, i
 #define MPR_MAXIT 50
 #define MPR_EPS 1e-10f
 
-__device__ __forceinline__ void normalize3(float* a) {
-  float n = sqrtf(dot3(a, a));
-  if (n < 1e-20f) { a[0] = 1; a[1] = a[2] = 0; return; }
-  float inv = 1.0f / n;
-  a[0] *= inv; a[1] *= inv; a[2] *= inv;
-}
 __device__ __forceinline__ void portal_dir(const Spt* p, float* dir) {
   float a[3] = {p[2].v[0] - p[1].v[0], p[2].v[1] - p[1].v[1], p[2].v[2] - p[1].v[2]};
   float b[3] = {p[3].v[0] - p[1].v[0], p[3].v[1] - p[1].v[1], p[3].v[2] - p[1].v[2]};
@@ -391,7 +569,7 @@ __device__ __forceinline__ bool reach_tolerance(const Spt* p, const Spt& v4, con
   float m1 = dv4 - dot3(p[1].v, dir), m2 = dv4 - dot3(p[2].v, dir), m3 = dv4 - dot3(p[3].v, dir);
   return fminf(fminf(m1, m2), m3) <= MPR_TOL;
 }
-__device__ float origin_tri_dist2(const float* a, const float* b, const float* c, float* w) {
+__device__ __noinline__ float origin_tri_dist2(const float* a, const float* b, const float* c, float* w) {
   float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
   float ap[3] = {-a[0], -a[1], -a[2]};
   float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
@@ -424,7 +602,7 @@ __device__ float origin_tri_dist2(const float* a, const float* b, const float* c
   w[0] = a[0] + ab[0] * v + ac[0] * u; w[1] = a[1] + ab[1] * v + ac[1] * u; w[2] = a[2] + ab[2] * v + ac[2] * u;
   return dot3(w, w);
 }
-__device__ void find_pos(const Spt* p, float* pos) {
+__device__ __noinline__ void find_pos(const Spt* p, float* pos) {
   float dir[3], b[4], t[3], sum;
   portal_dir(p, dir);
   cross3(t, p[1].v, p[2].v); b[0] = dot3(t, p[3].v);
@@ -447,126 +625,112 @@ __device__ void find_pos(const Spt* p, float* pos) {
   }
 }
 
-// Minkowski Portal Refinement; warp-uniform control flow, mesh support is lane-parallel
-__device__ bool mpr_penetration(const Cvx& A, const Cvx& B, float* depth, float* dir_out, float* pos, int lane) {
+// Minkowski Portal Refinement; warp-uniform control flow, mesh support is lane-parallel.
+// One support call site (phase machine) keeps the code small.
+__device__ __noinline__ bool mpr_penetration(const Cvx& A, const Cvx& B, float* depth, float* dir_out, float* pos, int lane) {
   Spt p[4], v4;
   float dir[3], va[3], vb[3];
   for (int k = 0; k < 3; k++) { p[0].v[k] = A.pos[k] - B.pos[k]; p[0].v1[k] = A.pos[k]; p[0].v2[k] = B.pos[k]; }
   if (fabsf(p[0].v[0]) < MPR_EPS && fabsf(p[0].v[1]) < MPR_EPS && fabsf(p[0].v[2]) < MPR_EPS) p[0].v[0] = 1e-5f;
   dir[0] = -p[0].v[0]; dir[1] = -p[0].v[1]; dir[2] = -p[0].v[2];
   normalize3(dir);
-  msupport(A, B, dir, p[1], lane);
-  if (dot3(p[1].v, dir) <= 0) return false;
-  cross3(dir, p[0].v, p[1].v);
-  if (dot3(dir, dir) < MPR_EPS * MPR_EPS) {
-    if (dot3(p[1].v, p[1].v) < MPR_EPS * MPR_EPS) { *depth = 0; dir_out[0] = dir_out[1] = dir_out[2] = 0; }
-    else { *depth = sqrtf(dot3(p[1].v, p[1].v)); dir_out[0] = p[1].v[0]; dir_out[1] = p[1].v[1]; dir_out[2] = p[1].v[2]; normalize3(dir_out); }
-    for (int k = 0; k < 3; k++) pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]);
-    return true;
-  }
-  normalize3(dir);
-  msupport(A, B, dir, p[2], lane);
-  if (dot3(p[2].v, dir) <= 0) return false;
-  for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
-  cross3(dir, va, vb); normalize3(dir);
-  if (dot3(dir, p[0].v) > 0) { Spt t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
-  for (int guard = 0;; guard++) {
-    if (guard > 100) return false;
-    msupport(A, B, dir, p[3], lane);
-    if (dot3(p[3].v, dir) <= 0) return false;
-    bool cont = false;
-    cross3(va, p[1].v, p[3].v);
-    if (dot3(va, p[0].v) < -MPR_EPS) { p[2] = p[3]; cont = true; }
-    if (!cont) {
-      cross3(va, p[3].v, p[2].v);
-      if (dot3(va, p[0].v) < -MPR_EPS) { p[1] = p[3]; cont = true; }
-    }
-    if (!cont) break;
-    for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
-    cross3(dir, va, vb); normalize3(dir);
-  }
-  for (int it = 0;; it++) {
-    portal_dir(p, dir);
-    if (dot3(dir, p[1].v) >= 0) break;
+  // phases: 0 -> v1, 1 -> v2, 2 -> v3 (portal discovery), 3 -> refinement, 4 -> penetration
+  int phase = 0, it = 0;
+  for (int guard = 0; guard < 3 * MPR_MAXIT + 120; guard++) {
     msupport(A, B, dir, v4, lane);
-    if (dot3(v4.v, dir) < 0 || reach_tolerance(p, v4, dir) || it > MPR_MAXIT) return false;
-    expand_portal(p, v4);
-  }
-  for (int it = 0;; it++) {
-    portal_dir(p, dir);
-    msupport(A, B, dir, v4, lane);
-    if (reach_tolerance(p, v4, dir) || it > MPR_MAXIT) {
-      float w[3];
-      float d2 = origin_tri_dist2(p[1].v, p[2].v, p[3].v, w);
-      *depth = sqrtf(d2);
-      if (*depth < MPR_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; }
-      else { dir_out[0] = w[0]; dir_out[1] = w[1]; dir_out[2] = w[2]; normalize3(dir_out); }
-      find_pos(p, pos);
-      return true;
+    if (phase == 0) {
+      p[1] = v4;
+      if (dot3(p[1].v, dir) <= 0) return false;
+      cross3(dir, p[0].v, p[1].v);
+      if (dot3(dir, dir) < MPR_EPS * MPR_EPS) {
+        if (dot3(p[1].v, p[1].v) < MPR_EPS * MPR_EPS) { *depth = 0; dir_out[0] = dir_out[1] = dir_out[2] = 0; }
+        else { *depth = sqrtf(dot3(p[1].v, p[1].v)); dir_out[0] = p[1].v[0]; dir_out[1] = p[1].v[1]; dir_out[2] = p[1].v[2]; normalize3(dir_out); }
+        for (int k = 0; k < 3; k++) pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]);
+        return true;
+      }
+      normalize3(dir);
+      phase = 1;
+    } else if (phase == 1) {
+      p[2] = v4;
+      if (dot3(p[2].v, dir) <= 0) return false;
+      for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+      cross3(dir, va, vb); normalize3(dir);
+      if (dot3(dir, p[0].v) > 0) { Spt t = p[1]; p[1] = p[2]; p[2] = t; dir[0] = -dir[0]; dir[1] = -dir[1]; dir[2] = -dir[2]; }
+      phase = 2; it = 0;
+    } else if (phase == 2) {
+      p[3] = v4;
+      if (dot3(p[3].v, dir) <= 0 || ++it > 100) return false;
+      bool cont = false;
+      cross3(va, p[1].v, p[3].v);
+      if (dot3(va, p[0].v) < -MPR_EPS) { p[2] = p[3]; cont = true; }
+      if (!cont) {
+        cross3(va, p[3].v, p[2].v);
+        if (dot3(va, p[0].v) < -MPR_EPS) { p[1] = p[3]; cont = true; }
+      }
+      if (cont) {
+        for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+        cross3(dir, va, vb); normalize3(dir);
+      } else {
+        portal_dir(p, dir);
+        it = 0;
+        phase = (dot3(dir, p[1].v) >= 0) ? 4 : 3;
+      }
+    } else if (phase == 3) {
+      if (dot3(v4.v, dir) < 0 || reach_tolerance(p, v4, dir) || it++ > MPR_MAXIT) return false;
+      expand_portal(p, v4);
+      portal_dir(p, dir);
+      if (dot3(dir, p[1].v) >= 0) { phase = 4; it = 0; }
+    } else {
+      if (reach_tolerance(p, v4, dir) || it++ > MPR_MAXIT) {
+        float w[3];
+        float d2 = origin_tri_dist2(p[1].v, p[2].v, p[3].v, w);
+        *depth = sqrtf(d2);
+        if (*depth < MPR_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; }
+        else { dir_out[0] = w[0]; dir_out[1] = w[1]; dir_out[2] = w[2]; normalize3(dir_out); }
+        find_pos(p, pos);
+        return true;
+      }
+      expand_portal(p, v4);
+      portal_dir(p, dir);
     }
-    expand_portal(p, v4);
   }
+  return false;
 }
 
-__device__ void make_cvx(const DevModel& m, const float* S, int cg, Cvx& c) {
+__device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int cg, Cvx& c) {
   const EnvLayout& o = m.L;
-  int b = m.cg_bodyid[cg];
-  c.type = m.cg_type[cg];
+  int b = PKI(cg_bodyid)[cg];
+  c.type = PKI(cg_type)[cg];
   const float* gp = S + o.gpos + 3 * cg;
   c.pos[0] = gp[0]; c.pos[1] = gp[1]; c.pos[2] = gp[2];
-  float q[4], gq[4] = {m.cg_quat[4 * cg], m.cg_quat[4 * cg + 1], m.cg_quat[4 * cg + 2], m.cg_quat[4 * cg + 3]};
-  quat_mul(q, S + o.xquat + 4 * b, gq);
+  float q[4];
+  quat_mul(q, S + o.xquat + 4 * b, PKF(cg_quat) + 4 * cg);
   quat_normalize(q);
   quat2mat(c.mat, q);
-  c.size[0] = m.cg_size[3 * cg]; c.size[1] = m.cg_size[3 * cg + 1]; c.size[2] = m.cg_size[3 * cg + 2];
+  c.size[0] = PKF(cg_size)[3 * cg]; c.size[1] = PKF(cg_size)[3 * cg + 1]; c.size[2] = PKF(cg_size)[3 * cg + 2];
   c.verts = nullptr; c.nvert = 0;
   if (c.type == GEOM_MESH) {
-    int mid = m.cg_dataid[cg];
-    c.verts = m.hull_vert + m.mesh_hulladr[mid]; c.nvert = m.mesh_hullnum[mid];
+    int mid = PKI(cg_dataid)[cg];
+    c.verts = m.hull_vert + PKI(mesh_hulladr)[mid]; c.nvert = PKI(mesh_hullnum)[mid];
   }
 }
 
-__device__ void add_contact(const DevModel& m, float* S, int& ncon, int& flags, int pair, float dist, const float* pos,
-                            const float* n, int lane) {
-  if (ncon >= m.maxcon) { flags |= 2; return; }
-  if (lane == 0) {
-    float* c = S + m.L.con + ncon * CON_STRIDE;
-    c[C_POS] = pos[0]; c[C_POS + 1] = pos[1]; c[C_POS + 2] = pos[2];
-    float x[3] = {n[0], n[1], n[2]}, y[3] = {0, 1, 0}, z[3];
-    if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
-    float d = dot3(x, y);
-    y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
-    normalize3(y);
-    cross3(z, x, y);
-    for (int k = 0; k < 3; k++) { c[C_FRAME + k] = x[k]; c[C_FRAME + 3 + k] = y[k]; c[C_FRAME + 6 + k] = z[k]; }
-    c[C_DIST] = dist; c[C_MU] = 0;
-    for (int k = 0; k < 5; k++) { c[C_FRICTION + k] = m.pair_friction[5 * pair + k]; c[C_SOLIMP + k] = m.pair_solimp[5 * pair + k]; }
-    c[C_SOLREF] = m.pair_solref[2 * pair]; c[C_SOLREF + 1] = m.pair_solref[2 * pair + 1];
-    c[C_DIM] = __int_as_float(m.pair_condim[pair]);
-    c[C_GEOM1] = __int_as_float(m.cg_geomid[m.pair_cg1[pair]]); c[C_GEOM2] = __int_as_float(m.cg_geomid[m.pair_cg2[pair]]);
-    c[C_EFC] = __int_as_float(-1);
-    c[C_BODY1] = __int_as_float(m.cg_bodyid[m.pair_cg1[pair]]); c[C_BODY2] = __int_as_float(m.cg_bodyid[m.pair_cg2[pair]]);
-    c[C_INCLMARGIN] = m.pair_margin[pair] - m.pair_gap[pair];
-  }
-  ncon++;
-}
+struct ContactOut { float dist[4], pos[4][3], n[3]; int count; };
 
-__device__ void narrowphase(const DevModel& m, float* S, int pair, int& ncon, int& flags, int lane) {
-  int c1 = m.pair_cg1[pair], c2 = m.pair_cg2[pair];
-  float margin = m.pair_margin[pair];
-  Cvx A, B;
-  make_cvx(m, S, c1, A);
-  make_cvx(m, S, c2, B);
+// analytic plane-vs-primitive routines and MPR for the rest; fills up to 4 contacts
+__device__ __noinline__ void narrow_pair(const Cvx& A, const Cvx& B, float margin, ContactOut& out, int lane) {
+  out.count = 0;
   if (A.type == GEOM_PLANE) {
     float n[3] = {A.mat[2], A.mat[5], A.mat[8]};
+    out.n[0] = n[0]; out.n[1] = n[1]; out.n[2] = n[2];
     float dif[3] = {B.pos[0] - A.pos[0], B.pos[1] - A.pos[1], B.pos[2] - A.pos[2]};
     if (B.type == GEOM_SPHERE) {
       float r = B.size[0], dist = dot3(dif, n) - r;
       if (dist > margin) return;
-      float pos[3] = {B.pos[0] - n[0] * (r + 0.5f * dist), B.pos[1] - n[1] * (r + 0.5f * dist), B.pos[2] - n[2] * (r + 0.5f * dist)};
-      add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
+      for (int k = 0; k < 3; k++) out.pos[0][k] = B.pos[k] - n[k] * (r + 0.5f * dist);
+      out.dist[0] = dist; out.count = 1;
     } else if (B.type == GEOM_CYLINDER) {
-      float axis[3] = {B.mat[2], B.mat[5], B.mat[8]}, vec[3], pos[3];
+      float axis[3] = {B.mat[2], B.mat[5], B.mat[8]}, vec[3];
       float r = B.size[0], h = B.size[1];
       float prjaxis = dot3(n, axis);
       if (prjaxis > 0) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }
@@ -579,12 +743,13 @@ __device__ void narrowphase(const DevModel& m, float* S, int pair, int& ncon, in
       axis[0] *= h; axis[1] *= h; axis[2] *= h; prjaxis *= h;
       float dist = dist0 + prjaxis + prjvec;
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) pos[k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
-      add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
+      int c = 0;
+      for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
+      out.dist[c++] = dist;
       dist = dist0 - prjaxis + prjvec;
       if (dist <= margin) {
-        for (int k = 0; k < 3; k++) pos[k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
-        add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
+        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
+        out.dist[c++] = dist;
       }
       float prjvec1 = -prjvec * 0.5f;
       dist = dist0 + prjaxis + prjvec1;
@@ -593,49 +758,54 @@ __device__ void narrowphase(const DevModel& m, float* S, int pair, int& ncon, in
         cross3(vec1, vec, axis); normalize3(vec1);
         float s = r * 0.8660254037844386f;
         vec1[0] *= s; vec1[1] *= s; vec1[2] *= s;
-        for (int k = 0; k < 3; k++) pos[k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-        add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
-        for (int k = 0; k < 3; k++) pos[k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-        add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
+        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+        out.dist[c++] = dist;
+        if (c < 4) {
+          for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+          out.dist[c++] = dist;
+        }
       }
+      out.count = c;
     } else if (B.type == GEOM_BOX) {
       float dist = dot3(dif, n);
-      int cnt = 0;
-      for (int i = 0; i < 8; i++) {
+      int c = 0;
+      for (int i = 0; i < 8 && c < 4; i++) {
         float l[3] = {(i & 1) ? B.size[0] : -B.size[0], (i & 2) ? B.size[1] : -B.size[1], (i & 4) ? B.size[2] : -B.size[2]};
-        float vec[3], pos[3];
+        float vec[3];
         mat_vec(vec, B.mat, l);
         float ldist = dot3(n, vec);
         if (dist + ldist > margin || ldist > 0) continue;
         float cd = dist + ldist;
-        for (int k = 0; k < 3; k++) pos[k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
-        add_contact(m, S, ncon, flags, pair, cd, pos, n, lane);
-        if (++cnt >= 4) break;
+        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
+        out.dist[c++] = cd;
       }
+      out.count = c;
     } else if (B.type == GEOM_MESH) {
       float nd[3] = {-n[0], -n[1], -n[2]}, s[3];
       support(B, nd, s, lane);
       float d3[3] = {s[0] - A.pos[0], s[1] - A.pos[1], s[2] - A.pos[2]};
       float dist = dot3(d3, n);
       if (dist > margin) return;
-      float pos[3] = {s[0] - n[0] * 0.5f * dist, s[1] - n[1] * 0.5f * dist, s[2] - n[2] * 0.5f * dist};
-      add_contact(m, S, ncon, flags, pair, dist, pos, n, lane);
+      for (int k = 0; k < 3; k++) out.pos[0][k] = s[k] - n[k] * 0.5f * dist;
+      out.dist[0] = dist; out.count = 1;
     }
   } else {
     float depth, dir[3], pos[3];
     if (!mpr_penetration(A, B, &depth, dir, pos, lane)) return;
     if (dot3(dir, dir) < 0.5f) return;
-    add_contact(m, S, ncon, flags, pair, -depth, pos, dir, lane);
+    out.n[0] = dir[0]; out.n[1] = dir[1]; out.n[2] = dir[2];
+    out.pos[0][0] = pos[0]; out.pos[0][1] = pos[1]; out.pos[0][2] = pos[2];
+    out.dist[0] = -depth; out.count = 1;
   }
 }
 
-__device__ void collision(const DevModel& m, float* S, int& ncon, int& flags, int lane) {
+__device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& flags, int lane) {
   const EnvLayout& o = m.L;
   float* gpos = S + o.gpos;
   for (int g = lane; g < m.ncgeom; g += 32) {
-    int b = m.cg_bodyid[g];
-    float t[3], lp[3] = {m.cg_pos[3 * g], m.cg_pos[3 * g + 1], m.cg_pos[3 * g + 2]};
-    mat_vec(t, S + o.xmat + 9 * b, lp);
+    int b = PKI(cg_bodyid)[g];
+    float t[3];
+    mat_vec(t, S + o.xmat + 9 * b, PKF(cg_pos) + 3 * g);
     gpos[3 * g] = S[o.xpos + 3 * b] + t[0]; gpos[3 * g + 1] = S[o.xpos + 3 * b + 1] + t[1]; gpos[3 * g + 2] = S[o.xpos + 3 * b + 2] + t[2];
   }
   __syncwarp();
@@ -644,52 +814,110 @@ __device__ void collision(const DevModel& m, float* S, int& ncon, int& flags, in
     int p = base + lane;
     bool pass = false;
     if (p < m.npair) {
-      int c1 = m.pair_cg1[p], c2 = m.pair_cg2[p];
-      float margin = m.pair_margin[p];
+      int pc = PKI(pair_cg)[p], c1 = pc & 0xffff, c2 = pc >> 16;
+      float margin = m.max_margin;
       float dif[3] = {gpos[3 * c2] - gpos[3 * c1], gpos[3 * c2 + 1] - gpos[3 * c1 + 1], gpos[3 * c2 + 2] - gpos[3 * c1 + 2]};
-      if (m.cg_type[c1] == GEOM_PLANE) {
-        int b = m.cg_bodyid[c1];
-        float q[4], gq[4] = {m.cg_quat[4 * c1], m.cg_quat[4 * c1 + 1], m.cg_quat[4 * c1 + 2], m.cg_quat[4 * c1 + 3]}, R[9];
-        quat_mul(q, S + o.xquat + 4 * b, gq);
+      // stage 1: bounding spheres; stage 2: oriented bounding boxes (6 face axes / lowest box corner
+      // against the plane).  Both are conservative: a rejected pair cannot produce a contact.
+      float q2[4], R2[9];
+      const float *ab2 = PKF(cg_aabb) + 6 * c2;
+      if (PKI(cg_type)[c1] == GEOM_PLANE) {
+        int b = PKI(cg_bodyid)[c1];
+        float q[4], R[9];
+        quat_mul(q, S + o.xquat + 4 * b, PKF(cg_quat) + 4 * c1);
         quat2mat(R, q);
         float n[3] = {R[2], R[5], R[8]};
-        pass = dot3(dif, n) <= m.cg_rbound[c2] + margin;
+        pass = dot3(dif, n) <= PKF(cg_rbound)[c2] + margin;
+        if (pass) {
+          quat_mul(q2, S + o.xquat + 4 * PKI(cg_bodyid)[c2], PKF(cg_quat) + 4 * c2);
+          quat_normalize(q2);
+          quat2mat(R2, q2);
+          float cw[3];
+          mat_vec(cw, R2, ab2);
+          float low = dot3(dif, n) + dot3(cw, n);
+          for (int k = 0; k < 3; k++) low -= fabsf(R2[k] * n[0] + R2[3 + k] * n[1] + R2[6 + k] * n[2]) * ab2[3 + k];
+          pass = low <= margin;
+        }
       } else {
-        float bound = m.cg_rbound[c1] + m.cg_rbound[c2] + margin;
+        float bound = PKF(cg_rbound)[c1] + PKF(cg_rbound)[c2] + margin;
         pass = dot3(dif, dif) <= bound * bound;
+        if (pass) {
+          float q1[4], R1[9], c1w[3], c2w[3];
+          const float* ab1 = PKF(cg_aabb) + 6 * c1;
+          quat_mul(q1, S + o.xquat + 4 * PKI(cg_bodyid)[c1], PKF(cg_quat) + 4 * c1);
+          quat_normalize(q1);
+          quat2mat(R1, q1);
+          quat_mul(q2, S + o.xquat + 4 * PKI(cg_bodyid)[c2], PKF(cg_quat) + 4 * c2);
+          quat_normalize(q2);
+          quat2mat(R2, q2);
+          mat_vec(c1w, R1, ab1);
+          mat_vec(c2w, R2, ab2);
+          float t[3] = {dif[0] + c2w[0] - c1w[0], dif[1] + c2w[1] - c1w[1], dif[2] + c2w[2] - c1w[2]};
+          for (int i = 0; i < 3 && pass; i++) {
+            float a1[3] = {R1[i], R1[3 + i], R1[6 + i]}, a2[3] = {R2[i], R2[3 + i], R2[6 + i]};
+            float r1 = ab1[3 + i] + margin, r2 = ab2[3 + i] + margin;
+            for (int k = 0; k < 3; k++) {
+              r1 += fabsf(R2[k] * a1[0] + R2[3 + k] * a1[1] + R2[6 + k] * a1[2]) * ab2[3 + k];
+              r2 += fabsf(R1[k] * a2[0] + R1[3 + k] * a2[1] + R1[6 + k] * a2[2]) * ab1[3 + k];
+            }
+            if (fabsf(dot3(t, a1)) > r1 || fabsf(dot3(t, a2)) > r2) pass = false;
+          }
+        }
       }
     }
     unsigned mask = __ballot_sync(FULL, pass);
     while (mask) {
       int bit = __ffs(mask) - 1;
       mask &= mask - 1;
-      narrowphase(m, S, base + bit, ncon, flags, lane);
+      int pair = base + bit;
+      int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
+      Cvx A, B;
+      ContactOut out;
+      make_cvx(m, S, c1, A);
+      make_cvx(m, S, c2, B);
+      narrow_pair(A, B, m.pair_margin[pair], out, lane);
+      for (int c = 0; c < out.count; c++) {
+        if (ncon >= m.maxcon) { flags |= 2; break; }
+        if (lane == 0) {
+          float* cr = S + o.con + ncon * CON_STRIDE;
+          float x[3] = {out.n[0], out.n[1], out.n[2]}, y[3] = {0, 1, 0}, z[3];
+          if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
+          float d = dot3(x, y);
+          y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
+          normalize3(y);
+          cross3(z, x, y);
+          for (int k = 0; k < 3; k++) { cr[C_POS + k] = out.pos[c][k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
+          cr[C_DIST] = out.dist[c]; cr[C_MU] = 0;
+          cr[C_DIM] = __int_as_float(m.pair_condim[pair]); cr[C_PAIR] = __int_as_float(pair); cr[C_EFC] = __int_as_float(-1);
+          cr[C_BODY1] = __int_as_float(PKI(cg_bodyid)[c1]); cr[C_BODY2] = __int_as_float(PKI(cg_bodyid)[c2]);
+          for (int k = 0; k < 5; k++) cr[C_FRICTION + k] = m.pair_friction[5 * pair + k];
+        }
+        ncon++;
+      }
     }
   }
   __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- S3/S5: velocity, bias, actuation
-__device__ void velocity_stage(const DevModel& m, float* S, int lane) {
+__device__ __forceinline__ void velocity_stage(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
   const float *cdof = S + o.cdof, *qvel = S + o.qvel, *cinert = S + o.cinert;
   float *cvel = S + o.cvel, *cdofdot = S + o.cdofdot, *cacc = S + o.cacc, *cfrc = S + o.cfrc;
   if (lane < 6) { cvel[lane] = 0; cfrc[lane] = 0; cacc[lane] = (lane < 3) ? 0.f : -m.gravity[lane - 3]; }
   __syncwarp();
-  // forward pass: body velocities, dof axis rates, bias accelerations, body forces
   for (int lv = 0; lv < m.nlevel; lv++) {
-    for (int idx = m.lvl_adr[lv] + lane; idx < m.lvl_adr[lv + 1]; idx += 32) {
-      int b = m.lvl_body[idx], p = m.body_parentid[b];
+    for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
+      int b = PKI(lvl_body)[idx], p = PKI(body_parentid)[b];
       float cv[6], ca[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) { cv[k] = cvel[6 * p + k]; ca[k] = cacc[6 * p + k]; }
-      int ja = m.body_jntadr[b];
-      for (int j = ja; j < ja + m.body_jntnum[b]; j++) {
-        int da = m.jnt_dofadr[j];
-        if (m.jnt_type[j] == JNT_FREE) {
-          for (int k = 0; k < 3; k++) {
+      int ja = PKI(body_jntadr)[b];
+      for (int j = ja; j < ja + PKI(body_jntnum)[b]; j++) {
+        int da = PKI(jnt_dofadr)[j];
+        if (PKI(jnt_type)[j] == JNT_FREE) {
+          for (int k = 0; k < 3; k++)
             for (int c = 0; c < 6; c++) { cdofdot[6 * (da + k) + c] = 0; cv[c] += cdof[6 * (da + k) + c] * qvel[da + k]; }
-          }
           for (int k = 3; k < 6; k++) {
             float cd[6];
             cross_motion(cd, cv, cdof + 6 * (da + k));
@@ -706,7 +934,7 @@ __device__ void velocity_stage(const DevModel& m, float* S, int lane) {
 #pragma unroll
       for (int k = 0; k < 6; k++) { cvel[6 * b + k] = cv[k]; cacc[6 * b + k] = ca[k]; }
       // body force; gravity compensation folded in by scaling this body's gravity term
-      float gc = m.body_gravcomp[b];
+      float gc = PKF(body_gravcomp)[b];
       float cae[6] = {ca[0], ca[1], ca[2], ca[3] + gc * m.gravity[0], ca[4] + gc * m.gravity[1], ca[5] + gc * m.gravity[2]};
       float f[6], t1[6], t2[6];
       mul_inert_vec(f, cinert + 10 * b, cae);
@@ -717,15 +945,14 @@ __device__ void velocity_stage(const DevModel& m, float* S, int lane) {
     }
     __syncwarp();
   }
-  // backward pass: parents gather children (cfrc holds own force; accumulate bottom-up)
   for (int lv = m.nlevel - 2; lv >= 0; lv--) {
-    for (int idx = m.lvl_adr[lv] + lane; idx < m.lvl_adr[lv + 1]; idx += 32) {
-      int b = m.lvl_body[idx];
+    for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
+      int b = PKI(lvl_body)[idx];
       float acc[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) acc[k] = cfrc[6 * b + k];
-      for (int c = m.child_adr[b]; c < m.child_adr[b + 1]; c++) {
-        const float* cc = cfrc + 6 * m.child_list[c];
+      for (int c = PKI(child_adr)[b]; c < PKI(child_adr)[b + 1]; c++) {
+        const float* cc = cfrc + 6 * PKI(child_list)[c];
 #pragma unroll
         for (int k = 0; k < 6; k++) acc[k] += cc[k];
       }
@@ -737,34 +964,34 @@ __device__ void velocity_stage(const DevModel& m, float* S, int lane) {
 }
 
 // qfrc_smooth = passive(springs, dampers) - bias(+gravcomp) + actuator ; also actuator length/velocity/force
-__device__ void smooth_forces(const DevModel& m, float* S, int lane) {
+__device__ __forceinline__ void smooth_forces(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
   const float *qpos = S + o.qpos, *qvel = S + o.qvel, *cdof = S + o.cdof, *cfrc = S + o.cfrc, *ctrl = S + o.ctrl;
   float *actforce = S + o.actforce, *actlen = S + o.actlen, *actvel = S + o.actvel, *qs = S + o.qfrc_smooth;
   int nv = m.nv;
   for (int a = lane; a < m.nu; a += 32) {
     float len = 0, vel = 0;
-    const float* mom = m.act_moment + a * nv;
+    const float* mom = PKF(act_moment) + a * nv;
     for (int d = 0; d < nv; d++) {
       float mm = mom[d];
-      if (mm != 0) { len += mm * qpos[m.dof_qposadr[d]]; vel += mm * qvel[d]; }
+      if (mm != 0) { len += mm * qpos[PKI(dof_qposadr)[d]]; vel += mm * qvel[d]; }
     }
     float c = ctrl[a];
-    if (m.actuator_ctrllimited[a]) c = fminf(fmaxf(c, m.actuator_ctrlrange[2 * a]), m.actuator_ctrlrange[2 * a + 1]);
-    float f = m.actuator_gainprm[3 * a] * c + m.actuator_biasprm[3 * a] + m.actuator_biasprm[3 * a + 1] * len +
-              m.actuator_biasprm[3 * a + 2] * vel;
-    if (m.actuator_forcelimited[a]) f = fminf(fmaxf(f, m.actuator_forcerange[2 * a]), m.actuator_forcerange[2 * a + 1]);
+    if (PKI(actuator_ctrllimited)[a]) c = fminf(fmaxf(c, PKF(actuator_ctrlrange)[2 * a]), PKF(actuator_ctrlrange)[2 * a + 1]);
+    const float *gp = PKF(actuator_gainprm) + 3 * a, *bp = PKF(actuator_biasprm) + 3 * a;
+    float f = gp[0] * c + bp[0] + bp[1] * len + bp[2] * vel;
+    if (PKI(actuator_forcelimited)[a]) f = fminf(fmaxf(f, PKF(actuator_forcerange)[2 * a]), PKF(actuator_forcerange)[2 * a + 1]);
     actlen[a] = len; actvel[a] = vel; actforce[a] = f;
   }
   __syncwarp();
   for (int i = lane; i < nv; i += 32) {
-    const float *c = cdof + 6 * i, *f = cfrc + 6 * m.dof_bodyid[i];
+    const float *c = cdof + 6 * i, *f = cfrc + 6 * PKI(dof_bodyid)[i];
     float bias = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
-    float q = -m.dof_damping[i] * qvel[i] - bias;
-    int j = m.dof_jntid[i];
-    float k = m.jnt_stiffness[j];
-    if (k != 0 && m.jnt_type[j] >= JNT_SLIDE) { int qa = m.jnt_qposadr[j]; q -= k * (qpos[qa] - m.qpos_spring[qa]); }
-    for (int a = 0; a < m.nu; a++) q += m.act_moment[a * nv + i] * actforce[a];
+    float q = -PKF(dof_damping)[i] * qvel[i] - bias;
+    int j = PKI(dof_jntid)[i];
+    float k = PKF(jnt_stiffness)[j];
+    if (k != 0 && PKI(jnt_type)[j] >= JNT_SLIDE) { int qa = PKI(jnt_qposadr)[j]; q -= k * (qpos[qa] - PKF(qpos_spring)[qa]); }
+    for (int a = 0; a < m.nu; a++) q += PKF(act_moment)[a * nv + i] * actforce[a];
     qs[i] = q;
     S[o.qacc_smooth + i] = q;
   }
@@ -786,14 +1013,14 @@ __device__ __forceinline__ float impedance(const float* solimp, float pos, float
   return dmin + y * (dmax - dmin);
 }
 
-// K, B of the reference acceleration from solref; returns R through *R
-__device__ __forceinline__ void row_params(const DevModel& m, const float* solref, const float* solimp, float pos,
-                                           float margin, float diag, float vel, float* R, float* aref) {
+// R and reference acceleration of one row from solref/solimp [upstream mj_makeImpedance, mj_referenceConstraint]
+__device__ __noinline__ void row_params(float timestep, const float* solref, const float* solimp, float pos, float margin,
+                                        float diag, float vel, float* R, float* aref) {
   float imp = impedance(solimp, pos, margin);
   *R = fmaxf(MINVAL, (1 - imp) / imp * diag);
   float K, B, dmax = fminf(fmaxf(solimp[1], MINIMP), MAXIMP);
   if (solref[0] > 0) {
-    float tc = fmaxf(solref[0], 2 * m.timestep), dr = solref[1];
+    float tc = fmaxf(solref[0], 2 * timestep), dr = solref[1];
     K = 1 / fmaxf(MINVAL, dmax * dmax * tc * tc * dr * dr);
     B = 2 / fmaxf(MINVAL, dmax * tc);
   } else {
@@ -803,86 +1030,82 @@ __device__ __forceinline__ void row_params(const DevModel& m, const float* solre
   *aref = -B * vel - K * imp * (pos - margin);
 }
 
-// Build constraint rows. Returns ns (simple rows) through ns_out and total rows through nefc_out.
-__device__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns_out, int& nefc_out, int& flags, int lane) {
+// Build constraint rows in the reference order: equality, friction loss, limits, contacts.
+__device__ __forceinline__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns_out, int& nefc_out, int& flags,
+                                                 int lane) {
   const EnvLayout& o = m.L;
   const float *qpos = S + o.qpos, *qvel = S + o.qvel;
   float *sc1 = S + o.s_c1, *sc2 = S + o.s_c2, *eR = S + o.e_R, *eD = S + o.e_D, *earef = S + o.e_aref, *efl = S + o.e_floss;
-  int *sd1 = (int*)(S + o.s_d1), *sd2 = (int*)(S + o.s_d2), *etype = (int*)(S + o.e_type), *eid = (int*)(S + o.e_id);
+  int *sd1 = (int*)(S + o.s_d1), *sd2 = (int*)(S + o.s_d2), *einfo = (int*)(S + o.e_info);
   int row0 = 0;
-  // equality (joint coupling, polynomial)
   {
     int nact = 0;
     for (int base = 0; base < m.neq; base += 32) {
       int e = base + lane;
-      bool act = e < m.neq && m.eq_active0[e];
+      bool act = e < m.neq && PKI(eq_active0)[e];
       unsigned mask = __ballot_sync(FULL, act);
       if (act) {
         int row = row0 + nact + __popc(mask & ((1u << lane) - 1));
-        int j1 = m.eq_obj1id[e], j2 = m.eq_obj2id[e];
-        const float* c = m.eq_data + 5 * e;
-        int q1 = m.jnt_qposadr[j1], d1 = m.jnt_dofadr[j1];
-        float pos, diag = m.dof_invweight0[d1], vel, c2 = 0;
+        int j1 = PKI(eq_obj1id)[e], j2 = PKI(eq_obj2id)[e];
+        const float* c = PKF(eq_data) + 5 * e;
+        int q1 = PKI(jnt_qposadr)[j1], d1 = PKI(jnt_dofadr)[j1];
+        float pos, diag = PKF(dof_invweight0)[d1], vel, c2 = 0;
         int d2 = -1;
         if (j2 >= 0) {
-          int q2 = m.jnt_qposadr[j2];
-          d2 = m.jnt_dofadr[j2];
-          float dif = qpos[q2] - m.qpos0[q2];
+          int q2 = PKI(jnt_qposadr)[j2];
+          d2 = PKI(jnt_dofadr)[j2];
+          float dif = qpos[q2] - PKF(qpos0)[q2];
           float poly = c[0] + dif * (c[1] + dif * (c[2] + dif * (c[3] + dif * c[4])));
           c2 = -(c[1] + dif * (2 * c[2] + dif * (3 * c[3] + dif * 4 * c[4])));
-          pos = qpos[q1] - m.qpos0[q1] - poly;
-          diag += m.dof_invweight0[d2];
+          pos = qpos[q1] - PKF(qpos0)[q1] - poly;
+          diag += PKF(dof_invweight0)[d2];
           vel = qvel[d1] + c2 * qvel[d2];
         } else {
-          pos = qpos[q1] - m.qpos0[q1] - c[0];
+          pos = qpos[q1] - PKF(qpos0)[q1] - c[0];
           vel = qvel[d1];
         }
         float R, aref;
-        row_params(m, m.eq_solref + 2 * e, m.eq_solimp + 5 * e, pos, 0.f, diag, vel, &R, &aref);
+        row_params(m.timestep, PKF(eq_solref) + 2 * e, PKF(eq_solimp) + 5 * e, pos, 0.f, diag, vel, &R, &aref);
         sd1[row] = d1; sc1[row] = 1.f; sd2[row] = d2; sc2[row] = c2;
-        eR[row] = R; eD[row] = 1.f / R; earef[row] = aref; efl[row] = 0; etype[row] = CNSTR_EQUALITY; eid[row] = e;
+        eR[row] = R; eD[row] = 1.f / R; earef[row] = aref; efl[row] = 0; einfo[row] = CNSTR_EQUALITY | (e << 8);
       }
       nact += __popc(mask);
     }
     row0 += nact;
   }
-  // friction loss
   for (int k = lane; k < m.nfloss; k += 32) {
-    int d = m.floss_list[k], row = row0 + k;
+    int d = PKI(floss_list)[k], row = row0 + k;
     float R, aref;
-    row_params(m, m.dof_solref + 2 * d, m.dof_solimp + 5 * d, 0.f, 0.f, m.dof_invweight0[d], qvel[d], &R, &aref);
+    row_params(m.timestep, PKF(dof_solref) + 2 * d, PKF(dof_solimp) + 5 * d, 0.f, 0.f, PKF(dof_invweight0)[d], qvel[d], &R, &aref);
     sd1[row] = d; sc1[row] = 1.f; sd2[row] = -1; sc2[row] = 0;
-    eR[row] = R; eD[row] = 1.f / R; earef[row] = aref; efl[row] = m.dof_frictionloss[d]; etype[row] = CNSTR_FRICTION; eid[row] = d;
+    eR[row] = R; eD[row] = 1.f / R; earef[row] = aref; efl[row] = PKF(dof_frictionloss)[d]; einfo[row] = CNSTR_FRICTION | (d << 8);
   }
   row0 += m.nfloss;
-  // joint limits (lower side first, then upper, joints in id order)
   for (int base = 0; base < m.nlimited; base += 32) {
     int k = base + lane;
     bool lo = false, hi = false;
     int j = 0, d = 0;
     float dlo = 0, dhi = 0, margin = 0;
     if (k < m.nlimited) {
-      j = m.limited_list[k]; d = m.jnt_dofadr[j];
-      float q = qpos[m.jnt_qposadr[j]];
-      margin = m.jnt_margin[j];
-      dlo = q - m.jnt_range[2 * j]; dhi = m.jnt_range[2 * j + 1] - q;
+      j = PKI(limited_list)[k]; d = PKI(jnt_dofadr)[j];
+      float q = qpos[PKI(jnt_qposadr)[j]];
+      margin = PKF(jnt_margin)[j];
+      dlo = q - PKF(jnt_range)[2 * j]; dhi = PKF(jnt_range)[2 * j + 1] - q;
       lo = dlo < margin; hi = dhi < margin;
     }
     unsigned mlo = __ballot_sync(FULL, lo), mhi = __ballot_sync(FULL, hi);
     unsigned below = (1u << lane) - 1;
     int r = row0 + __popc(mlo & below) + __popc(mhi & below);
-    if (lo) {
-      float R, aref;
-      row_params(m, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dlo, margin, m.dof_invweight0[d], qvel[d], &R, &aref);
-      sd1[r] = d; sc1[r] = 1.f; sd2[r] = -1; sc2[r] = 0;
-      eR[r] = R; eD[r] = 1.f / R; earef[r] = aref; efl[r] = 0; etype[r] = CNSTR_LIMIT; eid[r] = j;
-      r++;
-    }
-    if (hi) {
-      float R, aref;
-      row_params(m, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dhi, margin, m.dof_invweight0[d], -qvel[d], &R, &aref);
-      sd1[r] = d; sc1[r] = -1.f; sd2[r] = -1; sc2[r] = 0;
-      eR[r] = R; eD[r] = 1.f / R; earef[r] = aref; efl[r] = 0; etype[r] = CNSTR_LIMIT; eid[r] = j;
+    if (lo || hi) {
+      for (int side = 0; side < 2; side++) {
+        if (!(side ? hi : lo)) continue;
+        float R, aref, sg = side ? -1.f : 1.f;
+        row_params(m.timestep, PKF(jnt_solref) + 2 * j, PKF(jnt_solimp) + 5 * j, side ? dhi : dlo, margin, PKF(dof_invweight0)[d],
+                   sg * qvel[d], &R, &aref);
+        sd1[r] = d; sc1[r] = sg; sd2[r] = -1; sc2[r] = 0;
+        eR[r] = R; eD[r] = 1.f / R; earef[r] = aref; efl[r] = 0; einfo[r] = CNSTR_LIMIT | (j << 8);
+        r++;
+      }
     }
     row0 += __popc(mlo) + __popc(mhi);
   }
@@ -890,21 +1113,21 @@ __device__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns
   ns_out = ns;
   // contacts: dense Jacobian rows, lane = dof
   float* J = S + o.J;
-  const float *cdof = S + o.cdof, *rootcom = S + o.rootcom;
+  const float *cdof = S + o.cdof, *xpos = S + o.xpos;
   int crow = 0, nv = m.nv, ldj = o.ldj;
   for (int c = 0; c < ncon; c++) {
     float* con = S + o.con + c * CON_STRIDE;
     int dim = __float_as_int(con[C_DIM]);
     if (crow + dim > m.maxcrow) { flags |= 2; ncon = c; break; }
-    int b1 = __float_as_int(con[C_BODY1]), b2 = __float_as_int(con[C_BODY2]);
+    int b1 = __float_as_int(con[C_BODY1]), b2 = __float_as_int(con[C_BODY2]), pair = __float_as_int(con[C_PAIR]);
     float pos[3] = {con[C_POS], con[C_POS + 1], con[C_POS + 2]};
     for (int i = lane; i < nv; i += 32) {
-      bool in1 = (m.body_dofmask[2 * b1 + (i >> 5)] >> (i & 31)) & 1u, in2 = (m.body_dofmask[2 * b2 + (i >> 5)] >> (i & 31)) & 1u;
+      bool in1 = (PKI(body_dofmask)[2 * b1 + (i >> 5)] >> (i & 31)) & 1, in2 = (PKI(body_dofmask)[2 * b2 + (i >> 5)] >> (i & 31)) & 1;
       float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
       if (in1 != in2) {
         float sg = in2 ? 1.f : -1.f;
-        const float *cd = cdof + 6 * i, *com = rootcom + 3 * m.body_rootidx[m.dof_bodyid[i]];
-        float off[3] = {pos[0] - com[0], pos[1] - com[1], pos[2] - com[2]}, t[3];
+        const float *cd = cdof + 6 * i, *ref = xpos + 3 * PKI(root_list)[PKI(body_rootidx)[PKI(dof_bodyid)[i]]];
+        float off[3] = {pos[0] - ref[0], pos[1] - ref[1], pos[2] - ref[2]}, t[3];
         cross3(t, cd, off);
         jr[0] = sg * cd[0]; jr[1] = sg * cd[1]; jr[2] = sg * cd[2];
         jp[0] = sg * (cd[3] + t[0]); jp[1] = sg * (cd[4] + t[1]); jp[2] = sg * (cd[5] + t[2]);
@@ -920,13 +1143,14 @@ __device__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns
       const float* Jr = J + (crow + r) * ldj;
       float vel = 0;
       for (int i = 0; i < nv; i++) vel += Jr[i] * qvel[i];
-      float diag = (r < 3) ? (m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2])
-                           : (m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1]);
-      float R, aref;
-      row_params(m, con + C_SOLREF, con + C_SOLIMP, r == 0 ? con[C_DIST] : 0.f, r == 0 ? con[C_INCLMARGIN] : 0.f, diag, vel,
-                 &R, &aref);
+      float diag = (r < 3) ? (PKF(body_invweight0)[2 * b1] + PKF(body_invweight0)[2 * b2])
+                           : (PKF(body_invweight0)[2 * b1 + 1] + PKF(body_invweight0)[2 * b2 + 1]);
+      float R, aref, solref[2] = {m.pair_solref[2 * pair], m.pair_solref[2 * pair + 1]}, solimp[5];
+      for (int k = 0; k < 5; k++) solimp[k] = m.pair_solimp[5 * pair + k];
+      float inclmargin = m.pair_margin[pair] - m.pair_gap[pair];
+      row_params(m.timestep, solref, solimp, r == 0 ? con[C_DIST] : 0.f, r == 0 ? inclmargin : 0.f, diag, vel, &R, &aref);
       eR[row] = R; earef[row] = aref; efl[row] = 0;
-      etype[row] = (dim == 1) ? CNSTR_CONTACT_FRICTIONLESS : CNSTR_CONTACT_ELLIPTIC; eid[row] = c;
+      einfo[row] = ((dim == 1) ? CNSTR_CONTACT_FRICTIONLESS : CNSTR_CONTACT_ELLIPTIC) | (c << 8);
     }
     __syncwarp();
     if (lane == 0) {
@@ -947,195 +1171,7 @@ __device__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns
 }
 
 // ----------------------------------------------------------------------------- S7: Newton solver
-// Row-parallel evaluation of the constraint cost at jar (+ alpha*jv).
-// WRITE=true : alpha ignored (jar is current); writes force/state, returns cost in c.
-// WRITE=false: line-search probe; returns cost c, derivative g, curvature h (constraint part only).
-template <bool WRITE>
-__device__ void eval_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, float alpha, float& c_out,
-                                 float& g_out, float& h_out, int lane) {
-  const EnvLayout& o = m.L;
-  const float *jar = S + o.e_jar, *jv = S + o.e_jv, *eD = S + o.e_D, *eR = S + o.e_R, *efl = S + o.e_floss;
-  const int* etype = (const int*)(S + o.e_type);
-  float* force = S + o.e_force;
-  int* state = (int*)(S + o.e_state);
-  float c = 0, g = 0, h = 0;
-  for (int r = lane; r < nefc; r += 32) {
-    int tp = etype[r];
-    if (tp == CNSTR_CONTACT_ELLIPTIC) continue;
-    float D = eD[r], v = WRITE ? 0.f : jv[r], x = WRITE ? jar[r] : jar[r] + alpha * v;
-    float f = 0; int st = ST_SATISFIED;
-    if (tp == CNSTR_EQUALITY) {
-      c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC;
-    } else if (tp == CNSTR_FRICTION) {
-      float fl = efl[r], R = eR[r];
-      if (x <= -R * fl) { c += -0.5f * R * fl * fl - fl * x; g += -fl * v; f = fl; st = ST_LINEARNEG; }
-      else if (x >= R * fl) { c += -0.5f * R * fl * fl + fl * x; g += fl * v; f = -fl; st = ST_LINEARPOS; }
-      else { c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC; }
-    } else {  // limit or frictionless contact
-      if (x < 0) { c += 0.5f * D * x * x; g += D * x * v; h += D * v * v; f = -D * x; st = ST_QUADRATIC; }
-    }
-    if (WRITE) { force[r] = f; state[r] = st; }
-  }
-  for (int k = lane; k < ncon; k += 32) {
-    const float* con = S + o.con + k * CON_STRIDE;
-    int dim = __float_as_int(con[C_DIM]);
-    if (dim == 1) continue;
-    int i = __float_as_int(con[C_EFC]);
-    if (i < 0) continue;
-    float mu = con[C_MU];
-    float x0 = WRITE ? jar[i] : jar[i] + alpha * jv[i];
-    float N = x0 * mu, N1 = WRITE ? 0.f : jv[i] * mu, TT = 0, UV = 0, VV = 0;
-    for (int j = 1; j < dim; j++) {
-      float fj = con[C_FRICTION + j - 1];
-      float v = WRITE ? 0.f : jv[i + j] * fj, u = (WRITE ? jar[i + j] : jar[i + j] + alpha * jv[i + j]) * fj;
-      TT += u * u; UV += u * v; VV += v * v;
-    }
-    float T = sqrtf(TT);
-    if (N >= mu * T || (T <= 0 && N >= 0)) {
-      if (WRITE) for (int j = 0; j < dim; j++) { force[i + j] = 0; state[i + j] = ST_SATISFIED; }
-    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-      for (int j = 0; j < dim; j++) {
-        float D = eD[i + j], v = WRITE ? 0.f : jv[i + j], x = WRITE ? jar[i + j] : jar[i + j] + alpha * v;
-        c += 0.5f * D * x * x; g += D * x * v; h += D * v * v;
-        if (WRITE) { force[i + j] = -D * x; state[i + j] = ST_QUADRATIC; }
-      }
-    } else {
-      float Dm = eD[i] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
-      float NT = N - mu * T;
-      c += 0.5f * Dm * NT * NT;
-      if (WRITE) {
-        float f0 = -Dm * NT * mu;
-        force[i] = f0; state[i] = ST_CONE;
-        for (int j = 1; j < dim; j++) {
-          float fj = con[C_FRICTION + j - 1];
-          force[i + j] = -f0 / T * (jar[i + j] * fj) * fj; state[i + j] = ST_CONE;
-        }
-      } else {
-        float T1 = UV / T, T2d = (VV - T1 * T1) / T, NT1 = N1 - mu * T1;
-        g += Dm * NT * NT1; h += Dm * (NT1 * NT1 - NT * mu * T2d);
-      }
-    }
-  }
-  c_out = warp_sum(c);
-  if (!WRITE) { g_out = warp_sum(g); h_out = warp_sum(h); }
-  if (WRITE) __syncwarp();
-}
-
-// y[r] = J[r,:] . x for all rows (simple rows + dense contact rows)
-__device__ __forceinline__ void mul_J(const DevModel& m, const float* S, float* y, const float* x, int ns, int nefc, int lane) {
-  const EnvLayout& o = m.L;
-  const int *sd1 = (const int*)(S + o.s_d1), *sd2 = (const int*)(S + o.s_d2);
-  const float *sc1 = S + o.s_c1, *sc2 = S + o.s_c2, *J = S + o.J;
-  int nv = m.nv;
-  for (int r = lane; r < nefc; r += 32) {
-    float s;
-    if (r < ns) {
-      s = sc1[r] * x[sd1[r]];
-      int d2 = sd2[r];
-      if (d2 >= 0) s += sc2[r] * x[d2];
-    } else {
-      const float* Jr = J + (r - ns) * o.ldj;
-      s = 0;
-      for (int k = 0; k < nv; k++) s += Jr[k] * x[k];
-    }
-    y[r] = s;
-  }
-}
-
-// y[i] = sum_r J[r,i] f[r]
-__device__ __forceinline__ void mul_JT(const DevModel& m, const float* S, float* y, const float* f, int ns, int nefc, int lane) {
-  const EnvLayout& o = m.L;
-  const int *sd1 = (const int*)(S + o.s_d1), *sd2 = (const int*)(S + o.s_d2);
-  const float *sc1 = S + o.s_c1, *sc2 = S + o.s_c2, *J = S + o.J;
-  for (int i = lane; i < m.nv; i += 32) {
-    float s = 0;
-    for (int r = 0; r < ns; r++) {
-      if (sd1[r] == i) s += sc1[r] * f[r];
-      if (sd2[r] == i) s += sc2[r] * f[r];
-    }
-    for (int r = ns; r < nefc; r++) s += J[(r - ns) * o.ldj + i] * f[r];
-    y[i] = s;
-  }
-}
-
-// H = M + J^T D J over quadratic rows + elliptic cone blocks (lane i owns row i of the lower
-// triangle), then mirrored and Cholesky-factored in place.
-__device__ void build_hessian(const DevModel& m, float* S, int ns, int nefc, int lane) {
-  const EnvLayout& o = m.L;
-  const int *sd1 = (const int*)(S + o.s_d1), *sd2 = (const int*)(S + o.s_d2), *state = (const int*)(S + o.e_state),
-            *eid = (const int*)(S + o.e_id);
-  const float *sc1 = S + o.s_c1, *sc2 = S + o.s_c2, *J = S + o.J, *eD = S + o.e_D, *M = S + o.M, *jar = S + o.e_jar;
-  float *H = S + o.H, *tmpJ = S + o.tmpJ;
-  int nv = m.nv, ld = o.ldm, ldj = o.ldj;
-  for (int i = lane; i < nv; i += 32) {
-    float* Hi = H + i * ld;
-    const float* Mi = M + i * ld;
-    for (int k = 0; k <= i; k++) Hi[k] = Mi[k];
-    for (int r = 0; r < ns; r++) {
-      if (state[r] != ST_QUADRATIC) continue;
-      int d1 = sd1[r], d2 = sd2[r];
-      float D = eD[r], c1 = sc1[r], c2 = sc2[r];
-      if (d1 == i) Hi[i] += D * c1 * c1;
-      if (d2 == i) Hi[i] += D * c2 * c2;
-      if (d2 >= 0) {
-        int hi = max(d1, d2), lo = min(d1, d2);
-        if (hi == i) Hi[lo] += D * c1 * c2;
-      }
-    }
-  }
-  for (int r = ns; r < nefc; r++) {
-    int st = state[r];
-    if (st == ST_QUADRATIC) {
-      const float* Jr = J + (r - ns) * ldj;
-      float D = eD[r];
-      for (int i = lane; i < nv; i += 32) {
-        float s = D * Jr[i];
-        if (s != 0) {
-          float* Hi = H + i * ld;
-          for (int k = 0; k <= i; k++) Hi[k] += s * Jr[k];
-        }
-      }
-    } else if (st == ST_CONE) {
-      const float* con = S + o.con + eid[r] * CON_STRIDE;
-      int dim = __float_as_int(con[C_DIM]);
-      float mu = con[C_MU], U[6], sc[6], T2 = 0, Hc[36];
-      sc[0] = mu; U[0] = jar[r] * mu;
-      for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
-      float N = U[0], T = sqrtf(T2), Dm = eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
-      float iT = 1.0f / T;
-      Hc[0] = Dm;
-      for (int j = 1; j < dim; j++) Hc[j] = Hc[j * dim] = -Dm * mu * U[j] * iT;
-      for (int j = 1; j < dim; j++)
-        for (int k = 1; k < dim; k++)
-          Hc[j * dim + k] = Dm * (mu * N * U[j] * U[k] * iT * iT * iT - (j == k ? mu * (N - mu * T) * iT : 0.f));
-      for (int j = 0; j < dim; j++) for (int k = 0; k < dim; k++) Hc[j * dim + k] *= sc[j] * sc[k];
-      const float* Jc = J + (r - ns) * ldj;
-      __syncwarp();
-      for (int i = lane; i < nv; i += 32)
-        for (int j = 0; j < dim; j++) {
-          float t = 0;
-          for (int k = 0; k < dim; k++) t += Hc[j * dim + k] * Jc[k * ldj + i];
-          tmpJ[j * ldj + i] = t;
-        }
-      __syncwarp();
-      for (int i = lane; i < nv; i += 32) {
-        float* Hi = H + i * ld;
-        for (int j = 0; j < dim; j++) {
-          float s = Jc[j * ldj + i];
-          if (s != 0) {
-            const float* tj = tmpJ + j * ldj;
-            for (int k = 0; k <= i; k++) Hi[k] += s * tj[k];
-          }
-        }
-      }
-      r += dim - 1;
-    }
-  }
-  __syncwarp();
-  chol_factor(H, nv, ld, lane);
-}
-
-__device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane) {
+__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane) {
   const EnvLayout& o = m.L;
   int nv = m.nv;
   float *qacc = S + o.qacc, *Ma = S + o.v_Ma, *grad = S + o.v_grad, *search = S + o.v_search, *mv = S + o.v_mv;
@@ -1146,51 +1182,47 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     __syncwarp();
     return 0;
   }
+  Rows R;
+  R.sd1 = (const int*)(S + o.s_d1); R.sd2 = (const int*)(S + o.s_d2); R.info = (int*)(S + o.e_info);
+  R.sc1 = S + o.s_c1; R.sc2 = S + o.s_c2; R.J = S + o.J; R.eD = S + o.e_D; R.eR = S + o.e_R; R.efl = S + o.e_floss;
+  R.con = S + o.con; R.jar = jar; R.jv = jv; R.force = force; R.ns = ns; R.nefc = nefc; R.ncon = ncon; R.ldj = o.ldj; R.nv = nv;
   float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
   float cw, cs, dg, dh;
-  // warm start vs. unconstrained acceleration
+  // warm start vs. unconstrained acceleration: keep the cheaper one
   for (int i = lane; i < nv; i += 32) qacc[i] = warm[i];
   __syncwarp();
-  mul_J(m, S, jar, qacc, ns, nefc, lane);
+  mul_J(R, jar, qacc, lane);
   symv(Ma, M, qacc, nv, o.ldm, lane);
-  __syncwarp();
   for (int r = lane; r < nefc; r += 32) jar[r] -= aref[r];
   __syncwarp();
-  eval_constraints<true>(m, S, ns, nefc, ncon, 0.f, cw, dg, dh, lane);
+  eval_constraints<true>(R, 0.f, cw, dg, dh, lane);
   {
     float gsum = 0;
     for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
     cw += warp_sum(gsum);
   }
-  // cost at qacc_smooth: jar = J*qacc_smooth - aref (kept in jv scratch to avoid clobbering jar)
-  mul_J(m, S, jv, qas, ns, nefc, lane);
+  mul_J(R, jv, qas, lane);
+  for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
   __syncwarp();
-  {
-    // temporarily evaluate with jar := jv - aref via alpha trick: probe(jar'=jar_s)
-    for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
-    __syncwarp();
-    eval_constraints<false>(m, S, ns, nefc, ncon, 1.0f, cs, dg, dh, lane);
-  }
+  eval_constraints<false>(R, 1.0f, cs, dg, dh, lane);
   float cost = cw;
   if (!(cw <= cs)) {  // also catches NaN warm starts
     for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
     for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
     __syncwarp();
     symv(Ma, M, qacc, nv, o.ldm, lane);
-    __syncwarp();
-    eval_constraints<true>(m, S, ns, nefc, ncon, 0.f, cost, dg, dh, lane);
+    eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
   }
-  int iter = 0;  // `cost` = total objective (Gauss term is zero at qacc_smooth, included in cw)
+  int iter = 0;
   while (true) {
-    // gradient
-    mul_JT(m, S, qfc, force, ns, nefc, lane);
+    mul_JT(R, qfc, force, lane);
     float g2 = 0;
     for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
     g2 = warp_sum(g2);
     __syncwarp();
     if (iter >= m.iterations) break;
     if (iter > 0 && scale * sqrtf(g2) < m.tolerance) break;
-    build_hessian(m, S, ns, nefc, lane);
+    build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane);
     chol_solve(S + o.H, search, nv, o.ldm, lane);
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
@@ -1198,22 +1230,21 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     gs = warp_sum(gs); ss = warp_sum(ss);
     if (!(gs < 0) || scale * 0.5f * (-gs) < m.tolerance) break;
     symv(mv, M, search, nv, o.ldm, lane);
-    mul_J(m, S, jv, search, ns, nefc, lane);
-    __syncwarp();
+    mul_J(R, jv, search, lane);
     float q1 = 0, q2 = 0;
     for (int i = lane; i < nv; i += 32) { q1 += search[i] * (Ma[i] - qs[i]); q2 += search[i] * mv[i]; }
     q1 = warp_sum(q1); q2 = warp_sum(q2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
     float p0, p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
-    eval_constraints<false>(m, S, ns, nefc, ncon, 0.f, p0, p1, p2, lane);
+    eval_constraints<false>(R, 0.f, p0, p1, p2, lane);
     p1 += q1; p2 += q2;
     if (!(p1 < 0) || !(p2 > 0)) break;
     float d0 = p1;
     dlo = p1;
     a = -p1 / p2;
     for (int it = 0; it < m.ls_iterations; it++) {
-      eval_constraints<false>(m, S, ns, nefc, ncon, a, p0, p1, p2, lane);
+      eval_constraints<false>(R, a, p0, p1, p2, lane);
       p1 += q1 + a * q2; p2 += q2;
       if (fabsf(p1) < gtol || fabsf(p1) < 1e-6f * fabsf(d0)) break;
       if (p1 < 0) { lo = a; dlo = p1; } else { hi = a; dhi = p1; }
@@ -1234,7 +1265,7 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
     __syncwarp();
     float oldcost = cost;
-    eval_constraints<true>(m, S, ns, nefc, ncon, 0.f, cost, dg, dh, lane);
+    eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
     {
       float gsum = 0;
       for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
@@ -1243,8 +1274,7 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
     iter++;
     // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
     if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
-      mul_JT(m, S, qfc, force, ns, nefc, lane);
-      __syncwarp();
+      mul_JT(R, qfc, force, lane);
       break;
     }
   }
@@ -1252,7 +1282,7 @@ __device__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, 
 }
 
 // ----------------------------------------------------------------------------- S9: implicitfast + advance
-__device__ void integrate(const DevModel& m, float* S, int lane) {
+__device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
   int nv = m.nv, ld = o.ldm;
   float h = m.timestep;
@@ -1262,14 +1292,14 @@ __device__ void integrate(const DevModel& m, float* S, int lane) {
     float* Ai = A + i * ld;
     const float* Mi = M + i * ld;
     for (int k = 0; k <= i; k++) Ai[k] = Mi[k];
-    Ai[i] += h * m.dof_damping[i];
+    Ai[i] += h * PKF(dof_damping)[i];
     for (int a = 0; a < m.nu; a++) {
-      float b2 = m.actuator_biasprm[3 * a + 2];
+      float b2 = PKF(actuator_biasprm)[3 * a + 2];
       if (b2 == 0) continue;
-      if (m.actuator_forcelimited[a] &&
-          (actforce[a] <= m.actuator_forcerange[2 * a] || actforce[a] >= m.actuator_forcerange[2 * a + 1]))
+      if (PKI(actuator_forcelimited)[a] &&
+          (actforce[a] <= PKF(actuator_forcerange)[2 * a] || actforce[a] >= PKF(actuator_forcerange)[2 * a + 1]))
         continue;
-      const float* mom = m.act_moment + a * nv;
+      const float* mom = PKF(act_moment) + a * nv;
       float mi = mom[i];
       if (mi == 0) continue;
       float s = -h * b2 * mi;
@@ -1283,8 +1313,8 @@ __device__ void integrate(const DevModel& m, float* S, int lane) {
   for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
   __syncwarp();
   for (int j = lane; j < m.njnt; j += 32) {
-    int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-    if (m.jnt_type[j] == JNT_FREE) {
+    int qa = PKI(jnt_qposadr)[j], da = PKI(jnt_dofadr)[j];
+    if (PKI(jnt_type)[j] == JNT_FREE) {
       for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[da + k];
       float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
       float n = sqrtf(dot3(w, w));
@@ -1307,20 +1337,22 @@ __device__ void integrate(const DevModel& m, float* S, int lane) {
 }
 
 // ----------------------------------------------------------------------------- S4/S8: gyro + accelerometer
-__device__ void imu_sensors(const DevModel& m, float* S, float* sensordata_env, int lane) {
+// (runs after the solver: region X is free again, cacc is rebuilt there with qacc included)
+__device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* sensordata_env, int lane) {
   if (sensordata_env == nullptr) return;
   const EnvLayout& o = m.L;
   const float *cdof = S + o.cdof, *cdofdot = S + o.cdofdot, *qvel = S + o.qvel, *qacc = S + o.qacc;
   float* cacc = S + o.cacc;
-  // body accelerations with qacc (cacc[0] = -gravity is still in place)
+  if (lane < 6) cacc[lane] = (lane < 3) ? 0.f : -m.gravity[lane - 3];
+  __syncwarp();
   for (int lv = 0; lv < m.nlevel; lv++) {
-    for (int idx = m.lvl_adr[lv] + lane; idx < m.lvl_adr[lv + 1]; idx += 32) {
-      int b = m.lvl_body[idx], p = m.body_parentid[b];
+    for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
+      int b = PKI(lvl_body)[idx], p = PKI(body_parentid)[b];
       float ca[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) ca[k] = cacc[6 * p + k];
-      int da = m.body_dofadr[b];
-      for (int k = 0; k < m.body_dofnum[b]; k++)
+      int da = PKI(body_dofadr)[b];
+      for (int k = 0; k < PKI(body_dofnum)[b]; k++)
         for (int c = 0; c < 6; c++) ca[c] += cdofdot[6 * (da + k) + c] * qvel[da + k] + cdof[6 * (da + k) + c] * qacc[da + k];
 #pragma unroll
       for (int k = 0; k < 6; k++) cacc[6 * b + k] = ca[k];
@@ -1328,30 +1360,31 @@ __device__ void imu_sensors(const DevModel& m, float* S, float* sensordata_env, 
     __syncwarp();
   }
   for (int s = lane; s < m.nsensor; s += 32) {
-    int type = m.sensor_type[s];
+    int type = PKI(sensor_type)[s];
     if (type == SENS_RANGE) continue;
-    int site = m.sensor_objid[s], adr = m.sensor_adr[s], b = m.site_bodyid[site];
-    float q[4], sq[4] = {m.site_quat[4 * site], m.site_quat[4 * site + 1], m.site_quat[4 * site + 2], m.site_quat[4 * site + 3]};
-    float R[9], sp[3] = {m.site_pos[3 * site], m.site_pos[3 * site + 1], m.site_pos[3 * site + 2]}, p[3], t[3];
-    quat_mul(q, S + o.xquat + 4 * b, sq);
+    int site = PKI(sensor_objid)[s], adr = PKI(sensor_adr)[s], b = PKI(site_bodyid)[site];
+    float q[4], R[9], Rb[9], p[3], t[3];
+    quat_mul(q, S + o.xquat + 4 * b, PKF(site_quat) + 4 * site);
     quat_normalize(q);
     quat2mat(R, q);
-    mat_vec(t, S + o.xmat + 9 * b, sp);
+    quat2mat(Rb, S + o.xquat + 4 * b);
+    mat_vec(t, Rb, PKF(site_pos) + 3 * site);
     p[0] = S[o.xpos + 3 * b] + t[0]; p[1] = S[o.xpos + 3 * b + 1] + t[1]; p[2] = S[o.xpos + 3 * b + 2] + t[2];
-    const float *cv = S + o.cvel + 6 * b, *ca = cacc + 6 * b, *com = S + o.rootcom + 3 * m.body_rootidx[b];
+    const float *cv = S + o.cvel + 6 * b, *ca = cacc + 6 * b, *ref = S + o.xpos + 3 * PKI(root_list)[PKI(body_rootidx)[b]];
     float out[3];
     if (type == SENS_GYRO) {
       matT_vec(out, R, cv);
     } else {
-      float dif[3] = {p[0] - com[0], p[1] - com[1], p[2] - com[2]}, lin[3], vlin[3], al[3], wl[3], vl[3];
+      float dif[3] = {p[0] - ref[0], p[1] - ref[1], p[2] - ref[2]}, lin[3], vlin[3], al[3], wl[3], vl[3];
       cross3(t, ca, dif); lin[0] = ca[3] + t[0]; lin[1] = ca[4] + t[1]; lin[2] = ca[5] + t[2];
       cross3(t, cv, dif); vlin[0] = cv[3] + t[0]; vlin[1] = cv[4] + t[1]; vlin[2] = cv[5] + t[2];
       matT_vec(al, R, lin); matT_vec(wl, R, cv); matT_vec(vl, R, vlin);
       cross3(t, wl, vl);
       out[0] = al[0] + t[0]; out[1] = al[1] + t[1]; out[2] = al[2] + t[2];
     }
-    if (sensordata_env) { sensordata_env[adr] = out[0]; sensordata_env[adr + 1] = out[1]; sensordata_env[adr + 2] = out[2]; }
+    sensordata_env[adr] = out[0]; sensordata_env[adr + 1] = out[1]; sensordata_env[adr + 2] = out[2];
   }
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- kernel
@@ -1361,62 +1394,98 @@ __device__ __forceinline__ bool warp_bad(const float* x, int n, int lane) {
   return __any_sync(FULL, bad);
 }
 
-__device__ void reset_env(const DevModel& m, float* S, int lane) {
-  const EnvLayout& o = m.L;
-  for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = m.qpos0[i];
-  for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
-  __syncwarp();
-}
-
 struct FwdInfo { int ncon, ns, nefc, iter; };
 
-__device__ FwdInfo forward(const DevModel& m, float* S, int& flags, int lane) {
-  const EnvLayout& o = m.L;
-  FwdInfo fi;
-  kinematics(m, S, lane);
-  com_crb(m, S, lane);
-  collision(m, S, fi.ncon, flags, lane);
-  velocity_stage(m, S, lane);
-  smooth_forces(m, S, lane);
-  make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
-  // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
-  {
-    float *H = S + o.H;
-    const float* M = S + o.M;
-    for (int i = lane; i < m.nv; i += 32) for (int k = 0; k <= i; k++) H[i * o.ldm + k] = M[i * o.ldm + k];
-    __syncwarp();
-    chol_factor(H, m.nv, o.ldm, lane);
-    chol_solve(H, S + o.qacc_smooth, m.nv, o.ldm, lane);
+// TMA bulk copy of the model pack into shared memory (one elected thread issues, all wait)
+__device__ __forceinline__ void load_pack(const uint32_t* src, int nwords) {
+  __shared__ __align__(8) unsigned long long bar;
+  unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+  unsigned bytes = (unsigned)nwords * 4u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane);
-  for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
-  __syncwarp();
-  return fi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+    const unsigned CH = 16384;
+    for (unsigned off = 0; off < bytes; off += CH) {
+      unsigned n = bytes - off < CH ? bytes - off : CH;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                   "l"((const char*)src + off), "r"(n), "r"(bar_addr)
+                   : "memory");
+    }
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_PACK:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra DONE_PACK;\n"
+      "bra WAIT_PACK;\n"
+      "DONE_PACK:\n"
+      "}\n" ::"r"(bar_addr)
+      : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(256) ss_physics_kernel(DevModel m, StepArgs a) {
-  extern __shared__ float smem[];
+extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const DevModel m, const StepArgs a) {
   const EnvLayout& o = m.L;
+  load_pack(m.pack, m.pk.nwords);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  float* S = smem + (size_t)warp * o.total;
-  for (int env = blockIdx.x * wpb + warp; env < a.nenv; env += gridDim.x * wpb) {
+  float* S = smem + m.pk.nwords + (size_t)warp * o.total;
+  // Every warp of the CTA runs the same number of env iterations and steps so that the CTA-wide
+  // barriers below are uniform; the barriers keep the warps in the same code region, which is
+  // what makes the instruction cache work for this 100+ KB kernel (profiles/physics_r1.md).
+  int per = gridDim.x * wpb, trips = (a.nenv + per - 1) / per;
+#define STAGE_SYNC(level) do { if (a.sync_level >= (level) && attempt == 0) __syncthreads(); } while (0)
+  for (int trip = 0; trip < trips; trip++) {
+    int env = trip * per + blockIdx.x * wpb + warp;
+    bool active = env < a.nenv;
+    if (!active) env = a.nenv - 1;  // idle warps shadow the last env read-only and store nothing
     for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
     for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
     for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];
     __syncwarp();
     int flags = a.env_flags ? a.env_flags[env] : 0;
     float time = a.time ? a.time[env] : 0.f;
-    FwdInfo fi = {0, 0, 0, 0};
     int nsteps = a.forward_only ? 1 : a.nsteps;
     for (int s = 0; s < nsteps; s++) {
-      if (warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane)) { reset_env(m, S, lane); flags |= 1; }
-      fi = forward(m, S, flags, lane);
-      if (warp_bad(S + o.qacc, m.nv, lane)) {
-        reset_env(m, S, lane); flags |= 1;
-        fi = forward(m, S, flags, lane);
+      FwdInfo fi;
+      // mj_checkPos / mj_checkVel, then forward; mj_checkAcc re-runs forward once from the reset state
+      bool bad = warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane);
+      for (int attempt = 0; attempt < 2; attempt++) {
+        if (bad) {
+          for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
+          for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
+          __syncwarp();
+          flags |= 1;
+        }
+        STAGE_SYNC(1);
+        kinematics(m, S, lane);
+        STAGE_SYNC(2);
+        crb_mass_matrix(m, S, lane);
+        STAGE_SYNC(1);
+        collision(m, S, fi.ncon, flags, lane);
+        STAGE_SYNC(1);
+        velocity_stage(m, S, lane);
+        STAGE_SYNC(2);
+        smooth_forces(m, S, lane);
+        STAGE_SYNC(2);
+        make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
+        STAGE_SYNC(1);
+        // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
+        copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
+        chol_factor(S + o.H, m.nv, o.ldm, lane);
+        chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane);
+        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane);
+        for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
+        __syncwarp();
+        bad = warp_bad(S + o.qacc, m.nv, lane);
+        if (!bad) break;
       }
-      bool last = (s == nsteps - 1);
-      if (last) {
+      if (a.sync_level >= 1) __syncthreads();
+      if (s == nsteps - 1 && active) {
         // observations of the state the step started from (same convention as mjData after mj_step)
         imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
         if (a.xpos) for (int i = lane; i < m.nbody * 3; i += 32) a.xpos[(size_t)env * m.nbody * 3 + i] = S[o.xpos + i];
@@ -1432,8 +1501,9 @@ extern "C" __global__ void __launch_bounds__(256) ss_physics_kernel(DevModel m, 
             bool live = c < fi.ncon;
             size_t k = (size_t)env * m.maxcon + c;
             if (a.contact_geom) {
-              a.contact_geom[2 * k] = live ? __float_as_int(con[C_GEOM1]) : -1;
-              a.contact_geom[2 * k + 1] = live ? __float_as_int(con[C_GEOM2]) : -1;
+              int pc = live ? PKI(pair_cg)[__float_as_int(con[C_PAIR])] : 0;
+              a.contact_geom[2 * k] = live ? PKI(cg_geomid)[pc & 0xffff] : -1;
+              a.contact_geom[2 * k + 1] = live ? PKI(cg_geomid)[pc >> 16] : -1;
             }
             if (a.contact_dist) a.contact_dist[k] = live ? con[C_DIST] : 0.f;
             if (a.dbg_contact_pos) for (int t = 0; t < 3; t++) a.dbg_contact_pos[3 * k + t] = live ? con[C_POS + t] : 0.f;
@@ -1444,15 +1514,16 @@ extern "C" __global__ void __launch_bounds__(256) ss_physics_kernel(DevModel m, 
         if (a.dbg_qacc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qacc_smooth[(size_t)env * m.nv + i] = S[o.qacc_smooth + i];
         if (a.dbg_qfrc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_smooth[(size_t)env * m.nv + i] = S[o.qfrc_smooth + i];
         if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
+        __syncwarp();
       }
       if (!a.forward_only) { integrate(m, S, lane); time += m.timestep; }
     }
-    if (!a.forward_only) {
+    if (!a.forward_only && active) {
       for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
       for (int i = lane; i < m.nv; i += 32) { a.qvel[(size_t)env * m.nv + i] = S[o.qvel + i]; a.warm[(size_t)env * m.nv + i] = S[o.warm + i]; }
       if (a.time && lane == 0) a.time[env] = time;
     }
-    if (a.env_flags && lane == 0) a.env_flags[env] = flags;
+    if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
     __syncwarp();
   }
 }

@@ -1,0 +1,21 @@
+"""Tuning driver (not a test): times the cfg2 random-ctrl workload for the current SS_WPB / SS_SYNC."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import bench
+from stretch_mujoco_b200 import engine, blob
+raw = open(bench.GOLDEN, "rb").read()
+A, _ = blob.unpack(raw)
+dm = engine.DeviceModel(raw, 0)
+nenv = 4096
+B = engine.Batch(dm, nenv)
+dev = B.qpos.device
+lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev); hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
+for p in range(3):
+    B.ctrl.copy_(bench.ctrl_torch(0, 0, nenv, p, lo, hi, dev)); B.step(50)
+ms = []
+for p in range(3, 9):
+    B.ctrl.copy_(bench.ctrl_torch(0, 0, nenv, p, lo, hi, dev))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); B.step(50); e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
+print(f"SS_WPB={os.environ.get('SS_WPB','-')} SS_SYNC={os.environ.get('SS_SYNC','-')}: {np.mean(ms):.1f} ms/50 steps -> {nenv*50/np.mean(ms)*1e3:.0f} env-steps/s; checksum {B.qpos.abs().sum().item():.3f}")
