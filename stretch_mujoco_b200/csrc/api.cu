@@ -63,7 +63,7 @@ static int build_layout(DevModel& m) {
   auto take = [&](int n) { int r = off; off += (n + 3) & ~3; return r; };
   int nv = m.nv, nb = m.nbody;
   o.ldm = nv | 1;
-  o.ldj = nv | 1;
+  o.ldj = (nv + 3) & ~3;   // 16-byte aligned rows (float4 operand loads in the Hessian build)
   // live for the whole step
   o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv); o.qacc = take(nv);
   o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.cdof = take(nv * 6); o.cdofdot = take(nv * 6); o.cvel = take(nb * 6);

@@ -129,7 +129,7 @@ __device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld,
   for (int j = 0; j < n; j++) {
     float xj = x[j] / L[j * ld + j];
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
       if (i == j) x[i] = xj;
       else if (i > j) x[i] -= L[i * ld + j] * xj;
     }
@@ -138,7 +138,7 @@ __device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld,
   for (int j = n - 1; j >= 0; j--) {
     float xj = x[j] / L[j * ld + j];
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
       if (i == j) x[i] = xj;
       else if (i < j) x[i] -= L[j * ld + i] * xj;
     }
@@ -148,7 +148,7 @@ __device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld,
 
 // y = A x for the symmetric dense matrix in shared memory (full storage)
 __device__ __noinline__ void symv(float* y, const float* A, const float* x, int n, int ld, int lane) {
-  for (int i = lane; i < n; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
     float s = 0;
     const float* r = A + i * ld;
     for (int k = 0; k < n; k++) s += r[k] * x[k];
@@ -159,8 +159,53 @@ __device__ __noinline__ void symv(float* y, const float* A, const float* x, int 
 
 // copy the lower triangle of src into dst (row stride ld)
 __device__ __noinline__ void copy_lower(float* dst, const float* src, int n, int ld, int lane) {
-  for (int i = lane; i < n; i += 32)
+  _Pragma("unroll 1") for (int i = lane; i < n; i += 32)
     for (int k = 0; k <= i; k++) dst[i * ld + k] = src[i * ld + k];
+  __syncwarp();
+}
+
+// ---- n <= 32: one matrix row per lane held in REGISTERS, columns exchanged by warp shuffles ------------
+// Right-looking Cholesky on a register row a[0..31] (lane i = row i; entries k > i are don't-care).
+// 2 instructions per (row, column) pair, no shared-memory traffic and no dependent-load chains.
+__device__ __forceinline__ void chol_rows32(float (&a)[32], int n) {
+#pragma unroll
+  for (int j = 0; j < 32; j++) {  // rows >= n are identity rows: no guard, straight-line convergent code
+    float piv = __shfl_sync(FULL, a[j], j);
+    float l = a[j] * rsqrtf(fmaxf(piv, MINVAL));
+    a[j] = l;
+#pragma unroll
+    for (int k = j + 1; k < 32; k++) a[k] = fmaf(-l, __shfl_sync(FULL, l, k), a[k]);
+  }
+  (void)n;
+}
+// a += s * v[0..31] (v in shared memory, 16-byte aligned, zero padded to 32)
+__device__ __forceinline__ void rank1_row32(float (&a)[32], float s, const float* v) {
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    float4 t = v4[k];
+    a[4 * k] = fmaf(s, t.x, a[4 * k]); a[4 * k + 1] = fmaf(s, t.y, a[4 * k + 1]);
+    a[4 * k + 2] = fmaf(s, t.z, a[4 * k + 2]); a[4 * k + 3] = fmaf(s, t.w, a[4 * k + 3]);
+  }
+}
+// solve L L^T x = b in place (x in shared memory, L static in shared memory, running value in a register)
+__device__ __noinline__ void chol_solve32(const float* L, float* xs, int n, int ld, int lane) {
+  bool in = lane < n;
+  float x = in ? xs[lane] : 0.f, dinv = in ? 1.0f / L[lane * ld + lane] : 0.f;
+  const float* Lr = L + lane * ld;
+#pragma unroll 4
+  for (int j = 0; j < n; j++) {
+    float lij = (in && lane > j) ? Lr[j] : 0.f;
+    float xj = __shfl_sync(FULL, x * dinv, j);
+    x = (lane == j) ? xj : fmaf(-lij, xj, x);
+  }
+#pragma unroll 4
+  for (int j = n - 1; j >= 0; j--) {
+    float lji = (lane < j) ? L[j * ld + lane] : 0.f;
+    float xj = __shfl_sync(FULL, x * dinv, j);
+    x = (lane == j) ? xj : fmaf(-lji, xj, x);
+  }
+  if (in) xs[lane] = x;
   __syncwarp();
 }
 
@@ -183,7 +228,7 @@ template <bool WRITE>
 __device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& c_out, float& g_out, float& h_out, int lane) {
   const float *jar = R.jar, *jv = R.jv, *eD = R.eD, *eR = R.eR, *efl = R.efl;
   float c = 0, g = 0, h = 0;
-  for (int r = lane; r < R.nefc; r += 32) {
+  _Pragma("unroll 1") for (int r = lane; r < R.nefc; r += 32) {
     int inf = R.info[r], tp = INFO_TYPE(inf);
     if (tp == CNSTR_CONTACT_ELLIPTIC) continue;
     float D = eD[r], v = WRITE ? 0.f : jv[r], x = WRITE ? jar[r] : jar[r] + alpha * v;
@@ -200,7 +245,7 @@ __device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& 
     }
     if (WRITE) { R.force[r] = f; R.info[r] = (inf & ~0xF0) | (st << 4); }
   }
-  for (int k = lane; k < R.ncon; k += 32) {
+  _Pragma("unroll 1") for (int k = lane; k < R.ncon; k += 32) {
     const float* con = R.con + k * CON_STRIDE;
     int dim = __float_as_int(con[C_DIM]);
     if (dim == 1) continue;
@@ -252,7 +297,7 @@ __device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& 
 
 // y[r] = J[r,:] . x for all rows (simple rows + dense contact rows)
 __device__ __noinline__ void mul_J(const Rows R, float* y, const float* x, int lane) {
-  for (int r = lane; r < R.nefc; r += 32) {
+  _Pragma("unroll 1") for (int r = lane; r < R.nefc; r += 32) {
     float s;
     if (r < R.ns) {
       s = R.sc1[r] * x[R.sd1[r]];
@@ -270,7 +315,7 @@ __device__ __noinline__ void mul_J(const Rows R, float* y, const float* x, int l
 
 // y[i] = sum_r J[r,i] f[r]
 __device__ __noinline__ void mul_JT(const Rows R, float* y, const float* f, int lane) {
-  for (int i = lane; i < R.nv; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < R.nv; i += 32) {
     float s = 0;
     for (int r = 0; r < R.ns; r++) {
       if (R.sd1[r] == i) s += R.sc1[r] * f[r];
@@ -287,7 +332,7 @@ __device__ __noinline__ void mul_JT(const Rows R, float* y, const float* f, int 
 // triangle), then Cholesky-factored in place.
 __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane) {
   int nv = R.nv, ldj = R.ldj, ns = R.ns;
-  for (int i = lane; i < nv; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     float* Hi = H + i * ld;
     const float* Mi = M + i * ld;
     for (int k = 0; k <= i; k++) Hi[k] = Mi[k];
@@ -308,7 +353,7 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
     if (st == ST_QUADRATIC) {
       const float* Jr = R.J + (r - ns) * ldj;
       float D = R.eD[r];
-      for (int i = lane; i < nv; i += 32) {
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
         float s = D * Jr[i];
         if (s != 0) {
           float* Hi = H + i * ld;
@@ -331,14 +376,14 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
       for (int j = 0; j < dim; j++) for (int k = 0; k < dim; k++) Hc[j * dim + k] *= sc[j] * sc[k];
       const float* Jc = R.J + (r - ns) * ldj;
       __syncwarp();
-      for (int i = lane; i < nv; i += 32)
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32)
         for (int j = 0; j < dim; j++) {
           float t = 0;
           for (int k = 0; k < dim; k++) t += Hc[j * dim + k] * Jc[k * ldj + i];
           tmpJ[j * ldj + i] = t;
         }
       __syncwarp();
-      for (int i = lane; i < nv; i += 32) {
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
         float* Hi = H + i * ld;
         for (int j = 0; j < dim; j++) {
           float s = Jc[j * ldj + i];
@@ -353,6 +398,82 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
   }
   __syncwarp();
   chol_factor(H, nv, ld, lane);
+}
+
+// n <= 32 variant: the sparse rows are folded into a shared-memory copy of M, then lane i pulls row i
+// into registers, accumulates the dense contact rows as rank-1 updates (one unrolled body shared by
+// quadratic rows and cone blocks), factors in registers and writes only the factor L back.
+// With R.nefc == 0 this is a plain Cholesky factorisation of M into H (H may alias M).
+__device__ __noinline__ void build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane) {
+  int nv = R.nv, ldj = R.ldj, ns = R.ns;
+  if (lane < nv) {
+    float* Hi = H + lane * ld;
+    const float* Mi = M + lane * ld;
+#pragma unroll 1
+    for (int k = 0; k <= lane; k++) Hi[k] = Mi[k];
+#pragma unroll 1
+    for (int r = 0; r < ns; r++) {
+      if (INFO_STATE(R.info[r]) != ST_QUADRATIC) continue;
+      int d1 = R.sd1[r], d2 = R.sd2[r];
+      float D = R.eD[r], c1 = R.sc1[r], c2 = R.sc2[r];
+      if (d1 == lane) Hi[lane] += D * c1 * c1;
+      if (d2 == lane) Hi[lane] += D * c2 * c2;
+      if (d2 >= 0 && max(d1, d2) == lane) Hi[min(d1, d2)] += D * c1 * c2;
+    }
+  }
+  __syncwarp();
+  float h[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) h[k] = (lane < nv && k <= lane) ? H[lane * ld + k] : ((k == lane) ? 1.f : 0.f);
+#pragma unroll 1
+  for (int r = ns; r < R.nefc; r++) {
+    int inf = R.info[r], st = INFO_STATE(inf);
+    if (st == ST_QUADRATIC) {
+      const float* Jr = R.J + (r - ns) * ldj;
+      rank1_row32(h, (lane < nv) ? R.eD[r] * Jr[lane] : 0.f, Jr);
+    } else if (st == ST_CONE) {
+      const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+      int dim = __float_as_int(con[C_DIM]);
+      float mu = con[C_MU], U[6], sc[6], T2 = 0, Hc[36];
+      sc[0] = mu; U[0] = R.jar[r] * mu;
+#pragma unroll 1
+      for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = R.jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
+      float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
+      float iT = 1.0f / T;
+      const float* Jc = R.J + (r - ns) * ldj;
+      __syncwarp();
+      // tmp_j = sum_k Hc[j,k] J_k with Hc[j,k] = sc_j sc_k * d2s/dU_j dU_k (exact cone Hessian)
+#pragma unroll 1
+      for (int j = 0; j < dim; j++) {
+        float t = 0;
+#pragma unroll 1
+        for (int k = 0; k < dim; k++) {
+          float hjk;
+          if (j == 0 && k == 0) hjk = Dm;
+          else if (j == 0 || k == 0) hjk = -Dm * mu * U[j + k] * iT;
+          else hjk = Dm * (mu * N * U[j] * U[k] * iT * iT * iT - (j == k ? mu * (N - mu * T) * iT : 0.f));
+          t += hjk * sc[j] * sc[k] * Jc[k * ldj + lane];
+        }
+        tmpJ[j * ldj + lane] = t;   // lanes >= nv write the zero padding (J rows are zero padded)
+      }
+      (void)Hc;
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < dim; j++) rank1_row32(h, (lane < nv) ? Jc[j * ldj + lane] : 0.f, tmpJ + j * ldj);
+      r += dim - 1;
+    }
+  }
+  chol_rows32(h, nv);
+#pragma unroll
+  for (int k = 0; k < 32; k++) if (lane < nv && k <= lane) H[lane * ld + k] = h[k];
+  __syncwarp();
+}
+__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane) {
+  Rows R;
+  R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = 32;
+  R.sd1 = R.sd2 = nullptr; R.info = nullptr; R.sc1 = R.sc2 = R.J = R.eD = R.eR = R.efl = R.con = nullptr;
+  R.jar = R.jv = R.force = nullptr; R.ncon = 0;
+  build_hessian32(R, A, A, nullptr, ld, lane);
 }
 
 // ----------------------------------------------------------------------------- S1: kinematics + inertias + dof axes
@@ -465,7 +586,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
   const float *cinert = S + o.cinert, *cdof = S + o.cdof;
   float *crb = S + o.crb, *M = S + o.M;
   int nv = m.nv;
-  for (int k = lane; k < nv * o.ldm; k += 32) M[k] = 0;
+  _Pragma("unroll 1") for (int k = lane; k < nv * o.ldm; k += 32) M[k] = 0;
   for (int lv = m.nlevel - 1; lv >= 0; lv--) {
     for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
       int b = PKI(lvl_body)[idx];
@@ -482,7 +603,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
     }
     __syncwarp();
   }
-  for (int i = lane; i < nv; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     float buf[6];
     mul_inert_vec(buf, crb + 10 * PKI(dof_bodyid)[i], cdof + 6 * i);
     for (int j = i; j >= 0; j = PKI(dof_parentid)[j]) {
@@ -519,7 +640,7 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
   } else if (g.type == GEOM_MESH) {
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
 #pragma unroll 4
-    for (int i = lane; i < g.nvert; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < g.nvert; i += 32) {
       float4 v = __ldg(g.verts + i);
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
       if (s > best) { best = s; bi = i; }
@@ -802,7 +923,7 @@ __device__ __noinline__ void narrow_pair(const Cvx& A, const Cvx& B, float margi
 __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& flags, int lane) {
   const EnvLayout& o = m.L;
   float* gpos = S + o.gpos;
-  for (int g = lane; g < m.ncgeom; g += 32) {
+  _Pragma("unroll 1") for (int g = lane; g < m.ncgeom; g += 32) {
     int b = PKI(cg_bodyid)[g];
     float t[3];
     mat_vec(t, S + o.xmat + 9 * b, PKF(cg_pos) + 3 * g);
@@ -969,7 +1090,7 @@ __device__ __forceinline__ void smooth_forces(const DevModel& m, float* S, int l
   const float *qpos = S + o.qpos, *qvel = S + o.qvel, *cdof = S + o.cdof, *cfrc = S + o.cfrc, *ctrl = S + o.ctrl;
   float *actforce = S + o.actforce, *actlen = S + o.actlen, *actvel = S + o.actvel, *qs = S + o.qfrc_smooth;
   int nv = m.nv;
-  for (int a = lane; a < m.nu; a += 32) {
+  _Pragma("unroll 1") for (int a = lane; a < m.nu; a += 32) {
     float len = 0, vel = 0;
     const float* mom = PKF(act_moment) + a * nv;
     for (int d = 0; d < nv; d++) {
@@ -984,7 +1105,7 @@ __device__ __forceinline__ void smooth_forces(const DevModel& m, float* S, int l
     actlen[a] = len; actvel[a] = vel; actforce[a] = f;
   }
   __syncwarp();
-  for (int i = lane; i < nv; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     const float *c = cdof + 6 * i, *f = cfrc + 6 * PKI(dof_bodyid)[i];
     float bias = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
     float q = -PKF(dof_damping)[i] * qvel[i] - bias;
@@ -1073,7 +1194,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
     }
     row0 += nact;
   }
-  for (int k = lane; k < m.nfloss; k += 32) {
+  _Pragma("unroll 1") for (int k = lane; k < m.nfloss; k += 32) {
     int d = PKI(floss_list)[k], row = row0 + k;
     float R, aref;
     row_params(m.timestep, PKF(dof_solref) + 2 * d, PKF(dof_solimp) + 5 * d, 0.f, 0.f, PKF(dof_invweight0)[d], qvel[d], &R, &aref);
@@ -1121,7 +1242,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
     if (crow + dim > m.maxcrow) { flags |= 2; ncon = c; break; }
     int b1 = __float_as_int(con[C_BODY1]), b2 = __float_as_int(con[C_BODY2]), pair = __float_as_int(con[C_PAIR]);
     float pos[3] = {con[C_POS], con[C_POS + 1], con[C_POS + 2]};
-    for (int i = lane; i < nv; i += 32) {
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
       bool in1 = (PKI(body_dofmask)[2 * b1 + (i >> 5)] >> (i & 31)) & 1, in2 = (PKI(body_dofmask)[2 * b2 + (i >> 5)] >> (i & 31)) & 1;
       float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
       if (in1 != in2) {
@@ -1178,7 +1299,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   float *jar = S + o.e_jar, *jv = S + o.e_jv, *force = S + o.e_force, *qfc = S + o.qfrc_con;
   const float *qs = S + o.qfrc_smooth, *qas = S + o.qacc_smooth, *warm = S + o.warm, *M = S + o.M, *aref = S + o.e_aref;
   if (nefc == 0) {
-    for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qfc[i] = 0; }
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qfc[i] = 0; }
     __syncwarp();
     return 0;
   }
@@ -1189,26 +1310,26 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
   float cw, cs, dg, dh;
   // warm start vs. unconstrained acceleration: keep the cheaper one
-  for (int i = lane; i < nv; i += 32) qacc[i] = warm[i];
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = warm[i];
   __syncwarp();
   mul_J(R, jar, qacc, lane);
   symv(Ma, M, qacc, nv, o.ldm, lane);
-  for (int r = lane; r < nefc; r += 32) jar[r] -= aref[r];
+  _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] -= aref[r];
   __syncwarp();
   eval_constraints<true>(R, 0.f, cw, dg, dh, lane);
   {
     float gsum = 0;
-    for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
     cw += warp_sum(gsum);
   }
   mul_J(R, jv, qas, lane);
-  for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
+  _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
   __syncwarp();
   eval_constraints<false>(R, 1.0f, cs, dg, dh, lane);
   float cost = cw;
   if (!(cw <= cs)) {  // also catches NaN warm starts
-    for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
-    for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
+    _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
     __syncwarp();
     symv(Ma, M, qacc, nv, o.ldm, lane);
     eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
@@ -1217,22 +1338,22 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   while (true) {
     mul_JT(R, qfc, force, lane);
     float g2 = 0;
-    for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
     g2 = warp_sum(g2);
     __syncwarp();
     if (iter >= m.iterations) break;
     if (iter > 0 && scale * sqrtf(g2) < m.tolerance) break;
-    build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane);
-    chol_solve(S + o.H, search, nv, o.ldm, lane);
+    if (nv <= 32) { build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve32(S + o.H, search, nv, o.ldm, lane); }
+    else { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
-    for (int i = lane; i < nv; i += 32) { gs += grad[i] * search[i]; ss += search[i] * search[i]; }
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { gs += grad[i] * search[i]; ss += search[i] * search[i]; }
     gs = warp_sum(gs); ss = warp_sum(ss);
     if (!(gs < 0) || scale * 0.5f * (-gs) < m.tolerance) break;
     symv(mv, M, search, nv, o.ldm, lane);
     mul_J(R, jv, search, lane);
     float q1 = 0, q2 = 0;
-    for (int i = lane; i < nv; i += 32) { q1 += search[i] * (Ma[i] - qs[i]); q2 += search[i] * mv[i]; }
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { q1 += search[i] * (Ma[i] - qs[i]); q2 += search[i] * mv[i]; }
     q1 = warp_sum(q1); q2 = warp_sum(q2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
@@ -1261,14 +1382,14 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       a = an;
     }
     if (!(a > 0)) break;
-    for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
-    for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
+    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
+    _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
     __syncwarp();
     float oldcost = cost;
     eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
     {
       float gsum = 0;
-      for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
       cost += warp_sum(gsum);
     }
     iter++;
@@ -1288,7 +1409,7 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane)
   float h = m.timestep;
   float *A = S + o.H, *rhs = S + o.v_tmp, *qpos = S + o.qpos, *qvel = S + o.qvel;
   const float *M = S + o.M, *actforce = S + o.actforce;
-  for (int i = lane; i < nv; i += 32) {
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     float* Ai = A + i * ld;
     const float* Mi = M + i * ld;
     for (int k = 0; k <= i; k++) Ai[k] = Mi[k];
@@ -1308,11 +1429,11 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane)
     rhs[i] = S[o.qfrc_smooth + i] + S[o.qfrc_con + i];
   }
   __syncwarp();
-  chol_factor(A, nv, ld, lane);
-  chol_solve(A, rhs, nv, ld, lane);
-  for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
+  if (nv <= 32) { chol_factor32(A, nv, ld, lane); chol_solve32(A, rhs, nv, ld, lane); }
+  else { chol_factor(A, nv, ld, lane); chol_solve(A, rhs, nv, ld, lane); }
+  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
   __syncwarp();
-  for (int j = lane; j < m.njnt; j += 32) {
+  _Pragma("unroll 1") for (int j = lane; j < m.njnt; j += 32) {
     int qa = PKI(jnt_qposadr)[j], da = PKI(jnt_dofadr)[j];
     if (PKI(jnt_type)[j] == JNT_FREE) {
       for (int k = 0; k < 3; k++) qpos[qa + k] += h * qvel[da + k];
@@ -1359,7 +1480,7 @@ __device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* 
     }
     __syncwarp();
   }
-  for (int s = lane; s < m.nsensor; s += 32) {
+  _Pragma("unroll 1") for (int s = lane; s < m.nsensor; s += 32) {
     int type = PKI(sensor_type)[s];
     if (type == SENS_RANGE) continue;
     int site = PKI(sensor_objid)[s], adr = PKI(sensor_adr)[s], b = PKI(site_bodyid)[site];
@@ -1390,7 +1511,7 @@ __device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* 
 // ----------------------------------------------------------------------------- kernel
 __device__ __forceinline__ bool warp_bad(const float* x, int n, int lane) {
   bool bad = false;
-  for (int i = lane; i < n; i += 32) bad |= !(fabsf(x[i]) < MAXVAL);
+  _Pragma("unroll 1") for (int i = lane; i < n; i += 32) bad |= !(fabsf(x[i]) < MAXVAL);
   return __any_sync(FULL, bad);
 }
 
@@ -1438,14 +1559,14 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
   // barriers below are uniform; the barriers keep the warps in the same code region, which is
   // what makes the instruction cache work for this 100+ KB kernel (profiles/physics_r1.md).
   int per = gridDim.x * wpb, trips = (a.nenv + per - 1) / per;
-#define STAGE_SYNC(level) do { if (a.sync_level >= (level) && attempt == 0) __syncthreads(); } while (0)
+#define STAGE_SYNC(level) do { if (a.sync_level >= (level) && a.sync_level < 3 && attempt == 0) __syncthreads(); } while (0)
   for (int trip = 0; trip < trips; trip++) {
     int env = trip * per + blockIdx.x * wpb + warp;
     bool active = env < a.nenv;
     if (!active) env = a.nenv - 1;  // idle warps shadow the last env read-only and store nothing
-    for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
-    for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
-    for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];
+    _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
+    _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
+    _Pragma("unroll 1") for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];
     __syncwarp();
     int flags = a.env_flags ? a.env_flags[env] : 0;
     float time = a.time ? a.time[env] : 0.f;
@@ -1456,8 +1577,8 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
       bool bad = warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane);
       for (int attempt = 0; attempt < 2; attempt++) {
         if (bad) {
-          for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
-          for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
+          _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
+          _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
           __syncwarp();
           flags |= 1;
         }
@@ -1476,15 +1597,15 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
         STAGE_SYNC(1);
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
         copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
-        chol_factor(S + o.H, m.nv, o.ldm, lane);
-        chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane);
+        if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane); chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+        else { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane);
-        for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
+        _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();
         bad = warp_bad(S + o.qacc, m.nv, lane);
         if (!bad) break;
       }
-      if (a.sync_level >= 1) __syncthreads();
+      if (a.sync_level >= 3 ? (s % (a.sync_level - 2) == 0) : (a.sync_level >= 1)) __syncthreads();
       if (s == nsteps - 1 && active) {
         // observations of the state the step started from (same convention as mjData after mj_step)
         imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
@@ -1496,7 +1617,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
         if (a.ncon && lane == 0) a.ncon[env] = fi.ncon;
         if (a.solver_iter && lane == 0) a.solver_iter[env] = fi.iter;
         if (a.contact_geom || a.contact_dist || a.dbg_contact_pos || a.dbg_contact_normal)
-          for (int c = lane; c < m.maxcon; c += 32) {
+          _Pragma("unroll 1") for (int c = lane; c < m.maxcon; c += 32) {
             const float* con = S + o.con + c * CON_STRIDE;
             bool live = c < fi.ncon;
             size_t k = (size_t)env * m.maxcon + c;
@@ -1519,8 +1640,8 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
       if (!a.forward_only) { integrate(m, S, lane); time += m.timestep; }
     }
     if (!a.forward_only && active) {
-      for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
-      for (int i = lane; i < m.nv; i += 32) { a.qvel[(size_t)env * m.nv + i] = S[o.qvel + i]; a.warm[(size_t)env * m.nv + i] = S[o.warm + i]; }
+      _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
+      _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { a.qvel[(size_t)env * m.nv + i] = S[o.qvel + i]; a.warm[(size_t)env * m.nv + i] = S[o.warm + i]; }
       if (a.time && lane == 0) a.time[env] = time;
     }
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
