@@ -237,8 +237,9 @@ def run_ours(args):
     metrics = torch.stack([torch.tensor(float(nenv * MJ_STEPS_PER_STEP * K), device=dev), torch.tensor(total_ms, device=dev, dtype=torch.float32),
                            B.qpos.abs().sum(), B.ncon.sum().float(), (B.env_flags & 1).sum().float()]).float()
     if world > 1:
-        gathered = torch.empty(world, metrics.numel(), device=dev)
+        gathered = torch.empty(world * metrics.numel(), device=dev)
         dist.all_gather_into_tensor(gathered, metrics)
+        gathered = gathered.view(world, -1)
     else:
         gathered = metrics[None]
     if rank != 0:
