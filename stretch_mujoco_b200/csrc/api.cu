@@ -349,10 +349,12 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   memset(&B->dbg, 0, sizeof(B->dbg));
   B->dm = M->dm;
   DevModel& m = B->dm;
-  m.maxcon = maxcon > 0 ? maxcon : 16;
+  m.maxcon = maxcon > 0 ? maxcon : 24;
   int nsimple = m.neq + m.nfloss + 2 * m.nlimited;
   m.maxsimple = nsimple;
-  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 64;
+  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 96;
+  if (const char* e = getenv("SS_MAXCROW")) m.maxcrow = atoi(e);
+  if (const char* e = getenv("SS_MAXCON")) m.maxcon = atoi(e);
   m.maxrow = m.maxsimple + m.maxcrow;
   int floats = build_layout(m);
   B->smem_per_env = (size_t)floats * sizeof(float);
@@ -364,6 +366,16 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
   if (wpb < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
   wpb = std::min(wpb, 16);
+  {
+    // every warp of a CTA runs the same number of env iterations ("trips"): among the feasible warp
+    // counts prefer the one that wastes the fewest warp slots in the last trip
+    int best = wpb, best_cost = 1 << 30;
+    for (int w = wpb; w >= std::max(1, wpb - 3); w--) {
+      int per = sms * w, trips = (nenv + per - 1) / per, cost = trips * w;
+      if (cost < best_cost) { best_cost = cost; best = w; }
+    }
+    wpb = best;
+  }
   if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs
   B->sync_level = 1;
   if (const char* e = getenv("SS_SYNC")) B->sync_level = atoi(e);

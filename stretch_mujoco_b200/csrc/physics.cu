@@ -1572,9 +1572,9 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
     float time = a.time ? a.time[env] : 0.f;
     int nsteps = a.forward_only ? 1 : a.nsteps;
     for (int s = 0; s < nsteps; s++) {
-      FwdInfo fi;
+      FwdInfo fi = {0, 0, 0, 0};
       // mj_checkPos / mj_checkVel, then forward; mj_checkAcc re-runs forward once from the reset state
-      bool bad = warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane);
+      bool bad = active && (warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane));
       for (int attempt = 0; attempt < 2; attempt++) {
         if (bad) {
           _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
@@ -1583,26 +1583,28 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
           flags |= 1;
         }
         STAGE_SYNC(1);
-        kinematics(m, S, lane);
+        if (active) kinematics(m, S, lane);
         STAGE_SYNC(2);
-        crb_mass_matrix(m, S, lane);
+        if (active) crb_mass_matrix(m, S, lane);
         STAGE_SYNC(1);
-        collision(m, S, fi.ncon, flags, lane);
+        if (active) collision(m, S, fi.ncon, flags, lane);
         STAGE_SYNC(1);
-        velocity_stage(m, S, lane);
+        if (active) velocity_stage(m, S, lane);
         STAGE_SYNC(2);
-        smooth_forces(m, S, lane);
+        if (active) smooth_forces(m, S, lane);
         STAGE_SYNC(2);
-        make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
+        if (active) make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
         STAGE_SYNC(1);
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
+        if (active) {
         copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
         if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane); chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         else { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane);
         _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();
-        bad = warp_bad(S + o.qacc, m.nv, lane);
+        }
+        bad = active && warp_bad(S + o.qacc, m.nv, lane);
         if (!bad) break;
       }
       if (a.sync_level >= 3 ? (s % (a.sync_level - 2) == 0) : (a.sync_level >= 1)) __syncthreads();
@@ -1637,7 +1639,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
         if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
         __syncwarp();
       }
-      if (!a.forward_only) { integrate(m, S, lane); time += m.timestep; }
+      if (!a.forward_only && active) { integrate(m, S, lane); time += m.timestep; }
     }
     if (!a.forward_only && active) {
       _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];

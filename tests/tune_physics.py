@@ -18,4 +18,4 @@ for p in range(3, 9):
     B.ctrl.copy_(bench.ctrl_torch(0, 0, nenv, p, lo, hi, dev))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); B.step(50); e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
-print(f"SS_WPB={os.environ.get('SS_WPB','-')} SS_SYNC={os.environ.get('SS_SYNC','-')}: {np.mean(ms):.1f} ms/50 steps -> {nenv*50/np.mean(ms)*1e3:.0f} env-steps/s; checksum {B.qpos.abs().sum().item():.3f}")
+print(f"ncon max {int(B.ncon.max())} mean {float(B.ncon.float().mean()):.2f} p99 {float(torch.quantile(B.ncon.float(), 0.99)):.0f} | flags2={int((B.env_flags & 2).ne(0).sum())} SS_WPB={os.environ.get('SS_WPB','-')} SS_SYNC={os.environ.get('SS_SYNC','-')}: {np.mean(ms):.1f} ms/50 steps -> {nenv*50/np.mean(ms)*1e3:.0f} env-steps/s; checksum {B.qpos.abs().sum().item():.3f}")
