@@ -365,7 +365,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   size_t pack_bytes = (size_t)m.pk.nwords * 4 + 2048;  // + static shared (mbarrier, compiler scratch) slack
   int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
   if (wpb < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
-  wpb = std::min(wpb, 16);
+  wpb = std::min(wpb, 8);   // __launch_bounds__(256, 1): up to 255 registers per thread
   {
     // every warp of a CTA runs the same number of env iterations ("trips"): among the feasible warp
     // counts prefer the one that wastes the fewest warp slots in the last trip

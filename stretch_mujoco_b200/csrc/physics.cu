@@ -639,8 +639,8 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
     r[2] = l[2] > 0 ? g.size[1] : -g.size[1];
   } else if (g.type == GEOM_MESH) {
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
-#pragma unroll 4
-    _Pragma("unroll 1") for (int i = lane; i < g.nvert; i += 32) {
+#pragma unroll 8
+    for (int i = lane; i < g.nvert; i += 32) {
       float4 v = __ldg(g.verts + i);
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
       if (s > best) { best = s; bi = i; }
@@ -1550,7 +1550,7 @@ __device__ __forceinline__ void load_pack(const uint32_t* src, int nwords) {
       : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const DevModel m, const StepArgs a) {
+extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const DevModel m, const StepArgs a) {
   const EnvLayout& o = m.L;
   load_pack(m.pack, m.pk.nwords);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -1559,7 +1559,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
   // barriers below are uniform; the barriers keep the warps in the same code region, which is
   // what makes the instruction cache work for this 100+ KB kernel (profiles/physics_r1.md).
   int per = gridDim.x * wpb, trips = (a.nenv + per - 1) / per;
-#define STAGE_SYNC(level) do { if (a.sync_level >= (level) && a.sync_level < 3 && attempt == 0) __syncthreads(); } while (0)
+#define STAGE_SYNC(level) do { if ((a.sync_level == 5 ? 1 : a.sync_level) >= (level) && attempt == 0) __syncthreads(); } while (0)
   for (int trip = 0; trip < trips; trip++) {
     int env = trip * per + blockIdx.x * wpb + warp;
     bool active = env < a.nenv;
@@ -1582,7 +1582,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
           __syncwarp();
           flags |= 1;
         }
-        STAGE_SYNC(1);
+        if (a.sync_level != 5) STAGE_SYNC(1);
         if (active) kinematics(m, S, lane);
         STAGE_SYNC(2);
         if (active) crb_mass_matrix(m, S, lane);
@@ -1607,7 +1607,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) ss_physics_kernel(const Dev
         bad = active && warp_bad(S + o.qacc, m.nv, lane);
         if (!bad) break;
       }
-      if (a.sync_level >= 3 ? (s % (a.sync_level - 2) == 0) : (a.sync_level >= 1)) __syncthreads();
+      if (a.sync_level != 5 && a.sync_level >= 1 && a.sync_level < 3) __syncthreads();
       if (s == nsteps - 1 && active) {
         // observations of the state the step started from (same convention as mjData after mj_step)
         imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
