@@ -34,6 +34,47 @@ extern "C" const char* ss_version(void) { return "stretchsim 0.1.0 (sm_100a)"; }
 
 extern "C" __global__ void ss_physics_kernel(DevModel m, StepArgs a);
 
+// Env visiting order for the next physics launch: counting sort of the envs by the cost they
+// reported in the previous launch (Newton iterations + narrowphase queries), heaviest first.
+// Costs change slowly from one control period to the next, so consecutive slots hold envs of
+// similar cost.  The order only affects which warp simulates which env, never the results.
+__global__ void schedule_kernel(int nenv, const int32_t* __restrict__ cost, int nsteps_prev, int32_t* __restrict__ order,
+                                int32_t* __restrict__ work_counter) {
+  __shared__ int hist[256], start[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  if (nsteps_prev < 0) {  // SS_NOSORT=1: identity order (A/B knob)
+    for (int e = threadIdx.x; e < nenv; e += blockDim.x) order[e] = e;
+    if (threadIdx.x == 0) *work_counter = 0;
+    return;
+  }
+  int scale = nsteps_prev > 0 ? nsteps_prev : 1;
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&hist[255 - min(255, 4 * cost[e] / scale)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < 256; b++) { start[b] = acc; acc += hist[b]; }
+    *work_counter = 0;
+  }
+  __syncthreads();
+  // stable within a bucket: each warp-sized chunk of envs is placed in env order
+  for (int base = 0; base < nenv; base += blockDim.x) {
+    int e = base + threadIdx.x;
+    int b = e < nenv ? 255 - min(255, 4 * cost[e] / scale) : -1;
+    for (int w = 0; w < (int)blockDim.x / 32; w++) {
+      if ((int)threadIdx.x / 32 == w && b >= 0) {
+        unsigned peers = __match_any_sync(__activemask(), b);
+        int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+        int leader = __ffs(peers) - 1, pos = 0;
+        if ((int)(threadIdx.x & 31) == leader) pos = atomicAdd(&start[b], __popc(peers));
+        pos = __shfl_sync(peers, pos, leader);
+        order[pos + rank] = e;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- device upload helpers
 template <typename T>
 static const T* upload(ss_model* M, const std::vector<T>& v) {
@@ -366,31 +407,31 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
   if (wpb < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
   wpb = std::min(wpb, 8);   // __launch_bounds__(256, 1): up to 255 registers per thread
-  {
-    // every warp of a CTA runs the same number of env iterations ("trips"): among the feasible warp
-    // counts prefer the one that wastes the fewest warp slots in the last trip
-    int best = wpb, best_cost = 1 << 30;
-    for (int w = wpb; w >= std::max(1, wpb - 3); w--) {
-      int per = sms * w, trips = (nenv + per - 1) / per, cost = trips * w;
-      if (cost < best_cost) { best_cost = cost; best = w; }
-    }
-    wpb = best;
-  }
   if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs
-  B->sync_level = 1;
+  B->sync_level = 9;   // stage barriers (1) + CTA-uniform Newton loop (8), see physics.cu
   if (const char* e = getenv("SS_SYNC")) B->sync_level = atoi(e);
   B->pack_bytes = (size_t)m.pk.nwords * 4;
   B->warps_per_block = wpb;
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
   cudaError_t e = cudaFuncSetAttribute(ss_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B->pack_bytes + wpb * B->smem_per_env));
   if (e != cudaSuccess) { delete B; return ss_fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  if (cudaMalloc((void**)&B->order, sizeof(int32_t) * nenv) != cudaSuccess || cudaMalloc((void**)&B->cost, sizeof(int32_t) * nenv) != cudaSuccess ||
+      cudaMalloc((void**)&B->work_counter, sizeof(int32_t)) != cudaSuccess || cudaMemset(B->cost, 0, sizeof(int32_t) * nenv) != cudaSuccess) {
+    ss_batch_free(B);
+    return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  B->prev_nsteps = 1;
   *out = B;
   return 0;
 }
 
 extern "C" void ss_batch_free(ss_batch* B) {
   if (!B) return;
-  if (B->ray_xf) { cudaSetDevice(B->model->device); cudaFree(B->ray_xf); }
+  cudaSetDevice(B->model->device);
+  if (B->ray_xf) cudaFree(B->ray_xf);
+  if (B->order) cudaFree(B->order);
+  if (B->cost) cudaFree(B->cost);
+  if (B->work_counter) cudaFree(B->work_counter);
   delete B;
 }
 extern "C" long ss_batch_launch_count(const ss_batch* B) { return B ? B->launches : 0; }
@@ -417,8 +458,11 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   B->dm.iterations = B->model->dm.iterations;  // runtime-settable solver options (ss_model_set)
   B->dm.tolerance = B->model->dm.tolerance;
   size_t smem = B->pack_bytes + B->warps_per_block * B->smem_per_env;
+  a.order = B->order; a.cost = B->cost; a.work_counter = B->work_counter;
+  schedule_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(B->nenv, B->cost, getenv("SS_NOSORT") ? -1 : B->prev_nsteps, B->order, B->work_counter);
+  if (!forward_only) B->prev_nsteps = nsteps;
   ss_physics_kernel<<<B->grid, B->warps_per_block * 32, smem, (cudaStream_t)stream>>>(B->dm, a);
-  B->launches++;
+  B->launches += 2;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -13,4 +13,7 @@ struct StepArgs {
   // debug taps
   float *dbg_M, *dbg_qacc_smooth, *dbg_qfrc_smooth, *dbg_qfrc_constraint, *dbg_contact_pos, *dbg_contact_normal;
   int32_t* dbg_nefc;
+  // scheduling (library-owned): env visiting order (heaviest first), per-env cost of this launch, CTA work counter
+  const int32_t* order;
+  int32_t *cost, *work_counter;
 };

@@ -404,8 +404,13 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
 // into registers, accumulates the dense contact rows as rank-1 updates (one unrolled body shared by
 // quadratic rows and cone blocks), factors in registers and writes only the factor L back.
 // With R.nefc == 0 this is a plain Cholesky factorisation of M into H (H may alias M).
-__device__ __noinline__ void build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane) {
+// `work` = this warp has a matrix to factor; `sync` = CTA-wide barrier in front of the 1100-instruction
+// straight-line factorisation so that all warps of the CTA stream it through the instruction cache
+// together (every warp of the CTA must then make this call, working or not).
+__device__ __noinline__ void build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, bool sync) {
   int nv = R.nv, ldj = R.ldj, ns = R.ns;
+  float h[32];
+  if (work) {
   if (lane < nv) {
     float* Hi = H + lane * ld;
     const float* Mi = M + lane * ld;
@@ -422,7 +427,6 @@ __device__ __noinline__ void build_hessian32(const Rows R, float* H, const float
     }
   }
   __syncwarp();
-  float h[32];
 #pragma unroll
   for (int k = 0; k < 32; k++) h[k] = (lane < nv && k <= lane) ? H[lane * ld + k] : ((k == lane) ? 1.f : 0.f);
 #pragma unroll 1
@@ -434,7 +438,7 @@ __device__ __noinline__ void build_hessian32(const Rows R, float* H, const float
     } else if (st == ST_CONE) {
       const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
       int dim = __float_as_int(con[C_DIM]);
-      float mu = con[C_MU], U[6], sc[6], T2 = 0, Hc[36];
+      float mu = con[C_MU], U[6], sc[6], T2 = 0;
       sc[0] = mu; U[0] = R.jar[r] * mu;
 #pragma unroll 1
       for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = R.jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
@@ -456,24 +460,27 @@ __device__ __noinline__ void build_hessian32(const Rows R, float* H, const float
         }
         tmpJ[j * ldj + lane] = t;   // lanes >= nv write the zero padding (J rows are zero padded)
       }
-      (void)Hc;
       __syncwarp();
 #pragma unroll 1
       for (int j = 0; j < dim; j++) rank1_row32(h, (lane < nv) ? Jc[j * ldj + lane] : 0.f, tmpJ + j * ldj);
       r += dim - 1;
     }
   }
+  }
+  if (sync) __syncthreads();
+  if (work) {
   chol_rows32(h, nv);
 #pragma unroll
   for (int k = 0; k < 32; k++) if (lane < nv && k <= lane) H[lane * ld + k] = h[k];
   __syncwarp();
+  }
 }
-__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane) {
+__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane, bool work, bool sync) {
   Rows R;
   R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = 32;
   R.sd1 = R.sd2 = nullptr; R.info = nullptr; R.sc1 = R.sc2 = R.J = R.eD = R.eR = R.efl = R.con = nullptr;
   R.jar = R.jv = R.force = nullptr; R.ncon = 0;
-  build_hessian32(R, A, A, nullptr, ld, lane);
+  build_hessian32(R, A, A, nullptr, ld, lane, work, sync);
 }
 
 // ----------------------------------------------------------------------------- S1: kinematics + inertias + dof axes
@@ -619,7 +626,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
 
 // ----------------------------------------------------------------------------- S1c: collision
 struct Cvx {
-  int type, nvert;
+  int type, nvert, mesh;
   float pos[3], mat[9], size[3];
   const float4* verts;
 };
@@ -641,7 +648,7 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
 #pragma unroll 8
     for (int i = lane; i < g.nvert; i += 32) {
-      float4 v = __ldg(g.verts + i);
+      float4 v = g.verts[i];
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
       if (s > best) { best = s; bi = i; }
     }
@@ -650,7 +657,7 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
       float ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    float4 v = __ldg(g.verts + bi);
+    float4 v = g.verts[bi];
     r[0] = v.x; r[1] = v.y; r[2] = v.z;
   }
   mat_vec(out, g.mat, r);
@@ -829,10 +836,10 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
   quat_normalize(q);
   quat2mat(c.mat, q);
   c.size[0] = PKF(cg_size)[3 * cg]; c.size[1] = PKF(cg_size)[3 * cg + 1]; c.size[2] = PKF(cg_size)[3 * cg + 2];
-  c.verts = nullptr; c.nvert = 0;
+  c.verts = nullptr; c.nvert = 0; c.mesh = -1;
   if (c.type == GEOM_MESH) {
     int mid = PKI(cg_dataid)[cg];
-    c.verts = m.hull_vert + PKI(mesh_hulladr)[mid]; c.nvert = PKI(mesh_hullnum)[mid];
+    c.verts = m.hull_vert + PKI(mesh_hulladr)[mid]; c.nvert = PKI(mesh_hullnum)[mid]; c.mesh = mid;
   }
 }
 
@@ -920,7 +927,55 @@ __device__ __noinline__ void narrow_pair(const Cvx& A, const Cvx& B, float margi
   }
 }
 
-__device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& flags, int lane) {
+// Hull staging: MPR calls the support function of both hulls 20-60 times per query, each call a
+// scan over all hull vertices.  Instead of scanning them in global memory (L2 latency per call; the
+// L1 is carved down to ~30 KB by the shared-memory working sets) the pair's hulls are pulled once
+// into the env's not-yet-used Jacobian region by TMA bulk copies that complete on a per-warp
+// mbarrier.  Slot A (offset 0) is reused while consecutive pairs share their first geom.
+struct HullStage { float4* buf; int cap; unsigned bar; unsigned phase; int resA, nA; };
+
+__device__ __forceinline__ void stage_pair(HullStage& hs, Cvx& A, Cvx& B, int lane) {
+  bool needA = A.type == GEOM_MESH && A.nvert <= hs.cap && A.mesh != hs.resA;
+  if (A.type == GEOM_MESH && A.nvert > hs.cap) { hs.resA = -1; hs.nA = 0; }
+  if (A.type != GEOM_MESH) { hs.resA = -1; hs.nA = 0; }
+  if (needA) { hs.resA = A.mesh; hs.nA = A.nvert; }
+  bool stA = A.type == GEOM_MESH && hs.resA == A.mesh;
+  int offB = stA ? hs.nA : 0;
+  bool stB = B.type == GEOM_MESH && B.nvert <= hs.cap - offB;
+  unsigned bytes = (needA ? A.nvert * 16u : 0u) + (stB ? B.nvert * 16u : 0u);
+  if (bytes) {
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hs.bar), "r"(bytes) : "memory");
+      if (needA)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(hs.buf)),
+                     "l"(A.verts), "r"(A.nvert * 16u), "r"(hs.bar)
+                     : "memory");
+      if (stB)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(hs.buf + offB)),
+                     "l"(B.verts), "r"(B.nvert * 16u), "r"(hs.bar)
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_HULL:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_HULL;\n"
+        "bra WAIT_HULL;\n"
+        "DONE_HULL:\n"
+        "}\n" ::"r"(hs.bar), "r"(hs.phase)
+        : "memory");
+    hs.phase ^= 1u;
+  }
+  if (stA) A.verts = hs.buf;
+  if (stB) B.verts = hs.buf + offB;
+}
+
+__device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& nnarrow, int& flags, HullStage& hs, int lane) {
   const EnvLayout& o = m.L;
   float* gpos = S + o.gpos;
   _Pragma("unroll 1") for (int g = lane; g < m.ncgeom; g += 32) {
@@ -931,6 +986,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
   }
   __syncwarp();
   ncon = 0;
+  hs.resA = -1; hs.nA = 0;   // the Jacobian region was overwritten since the previous step
   for (int base = 0; base < m.npair; base += 32) {
     int p = base + lane;
     bool pass = false;
@@ -987,6 +1043,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       }
     }
     unsigned mask = __ballot_sync(FULL, pass);
+    nnarrow += __popc(mask);
     while (mask) {
       int bit = __ffs(mask) - 1;
       mask &= mask - 1;
@@ -996,6 +1053,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       ContactOut out;
       make_cvx(m, S, c1, A);
       make_cvx(m, S, c2, B);
+      if (A.type != GEOM_PLANE) stage_pair(hs, A, B, lane);
       narrow_pair(A, B, m.pair_margin[pair], out, lane);
       for (int c = 0; c < out.count; c++) {
         if (ncon >= m.maxcon) { flags |= 2; break; }
@@ -1292,16 +1350,19 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
 }
 
 // ----------------------------------------------------------------------------- S7: Newton solver
-__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane) {
+// Every warp of the CTA makes this call (`active` = it owns an env).  With `sync` the Newton loop is
+// CTA-uniform: the warps meet before the gradient, the Hessian and the line search of every iteration
+// (converged warps only keep the barriers company), which lets them share instruction-cache lines.
+__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, bool sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv;
   float *qacc = S + o.qacc, *Ma = S + o.v_Ma, *grad = S + o.v_grad, *search = S + o.v_search, *mv = S + o.v_mv;
   float *jar = S + o.e_jar, *jv = S + o.e_jv, *force = S + o.e_force, *qfc = S + o.qfrc_con;
   const float *qs = S + o.qfrc_smooth, *qas = S + o.qacc_smooth, *warm = S + o.warm, *M = S + o.M, *aref = S + o.e_aref;
-  if (nefc == 0) {
+  bool done = !active || nefc == 0;
+  if (active && nefc == 0) {
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] = qas[i]; qfc[i] = 0; }
     __syncwarp();
-    return 0;
   }
   Rows R;
   R.sd1 = (const int*)(S + o.s_d1); R.sd2 = (const int*)(S + o.s_d2); R.info = (int*)(S + o.e_info);
@@ -1309,6 +1370,8 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   R.con = S + o.con; R.jar = jar; R.jv = jv; R.force = force; R.ns = ns; R.nefc = nefc; R.ncon = ncon; R.ldj = o.ldj; R.nv = nv;
   float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
   float cw, cs, dg, dh;
+  float cost = 0;
+  if (!done) {
   // warm start vs. unconstrained acceleration: keep the cheaper one
   _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = warm[i];
   __syncwarp();
@@ -1326,7 +1389,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
   __syncwarp();
   eval_constraints<false>(R, 1.0f, cs, dg, dh, lane);
-  float cost = cw;
+  cost = cw;
   if (!(cw <= cs)) {  // also catches NaN warm starts
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
@@ -1334,22 +1397,30 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     symv(Ma, M, qacc, nv, o.ldm, lane);
     eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
   }
+  }
   int iter = 0;
   while (true) {
-    mul_JT(R, qfc, force, lane);
-    float g2 = 0;
-    _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
-    g2 = warp_sum(g2);
-    __syncwarp();
-    if (iter >= m.iterations) break;
-    if (iter > 0 && scale * sqrtf(g2) < m.tolerance) break;
-    if (nv <= 32) { build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve32(S + o.H, search, nv, o.ldm, lane); }
-    else { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
+    if (sync) { if (!__syncthreads_or(!done)) break; } else if (done) break;
+    if (!done) {
+      mul_JT(R, qfc, force, lane);
+      float g2 = 0;
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
+      g2 = warp_sum(g2);
+      __syncwarp();
+      if (iter >= m.iterations) done = true;
+      else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
+    }
+    if (nv <= 32) {
+      build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane, !done, sync);
+      if (!done) chol_solve32(S + o.H, search, nv, o.ldm, lane);
+    } else if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
+    if (sync) __syncthreads();
+    if (done) continue;
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { gs += grad[i] * search[i]; ss += search[i] * search[i]; }
     gs = warp_sum(gs); ss = warp_sum(ss);
-    if (!(gs < 0) || scale * 0.5f * (-gs) < m.tolerance) break;
+    if (!(gs < 0) || scale * 0.5f * (-gs) < m.tolerance) { done = true; continue; }
     symv(mv, M, search, nv, o.ldm, lane);
     mul_J(R, jv, search, lane);
     float q1 = 0, q2 = 0;
@@ -1360,7 +1431,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     float p0, p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
     eval_constraints<false>(R, 0.f, p0, p1, p2, lane);
     p1 += q1; p2 += q2;
-    if (!(p1 < 0) || !(p2 > 0)) break;
+    if (!(p1 < 0) || !(p2 > 0)) { done = true; continue; }
     float d0 = p1;
     dlo = p1;
     a = -p1 / p2;
@@ -1381,7 +1452,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       }
       a = an;
     }
-    if (!(a > 0)) break;
+    if (!(a > 0)) { done = true; continue; }
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
     __syncwarp();
@@ -1396,20 +1467,20 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
     if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
       mul_JT(R, qfc, force, lane);
-      break;
+      done = true;
     }
   }
   return iter;
 }
 
 // ----------------------------------------------------------------------------- S9: implicitfast + advance
-__device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane) {
+__device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane, bool active, bool sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv, ld = o.ldm;
   float h = m.timestep;
   float *A = S + o.H, *rhs = S + o.v_tmp, *qpos = S + o.qpos, *qvel = S + o.qvel;
   const float *M = S + o.M, *actforce = S + o.actforce;
-  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
+  if (active) _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     float* Ai = A + i * ld;
     const float* Mi = M + i * ld;
     for (int k = 0; k <= i; k++) Ai[k] = Mi[k];
@@ -1429,8 +1500,9 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane)
     rhs[i] = S[o.qfrc_smooth + i] + S[o.qfrc_con + i];
   }
   __syncwarp();
-  if (nv <= 32) { chol_factor32(A, nv, ld, lane); chol_solve32(A, rhs, nv, ld, lane); }
-  else { chol_factor(A, nv, ld, lane); chol_solve(A, rhs, nv, ld, lane); }
+  if (nv <= 32) { chol_factor32(A, nv, ld, lane, active, sync); if (active) chol_solve32(A, rhs, nv, ld, lane); }
+  else if (active) { chol_factor(A, nv, ld, lane); chol_solve(A, rhs, nv, ld, lane); }
+  if (!active) return;
   _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
   __syncwarp();
   _Pragma("unroll 1") for (int j = lane; j < m.njnt; j += 32) {
@@ -1515,7 +1587,7 @@ __device__ __forceinline__ bool warp_bad(const float* x, int n, int lane) {
   return __any_sync(FULL, bad);
 }
 
-struct FwdInfo { int ncon, ns, nefc, iter; };
+struct FwdInfo { int ncon, ns, nefc, iter, nnarrow; };
 
 // TMA bulk copy of the model pack into shared memory (one elected thread issues, all wait)
 __device__ __forceinline__ void load_pack(const uint32_t* src, int nwords) {
@@ -1555,15 +1627,32 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
   load_pack(m.pack, m.pk.nwords);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* S = smem + m.pk.nwords + (size_t)warp * o.total;
-  // Every warp of the CTA runs the same number of env iterations and steps so that the CTA-wide
-  // barriers below are uniform; the barriers keep the warps in the same code region, which is
-  // what makes the instruction cache work for this 100+ KB kernel (profiles/physics_r1.md).
-  int per = gridDim.x * wpb, trips = (a.nenv + per - 1) / per;
-#define STAGE_SYNC(level) do { if ((a.sync_level == 5 ? 1 : a.sync_level) >= (level) && attempt == 0) __syncthreads(); } while (0)
-  for (int trip = 0; trip < trips; trip++) {
-    int env = trip * per + blockIdx.x * wpb + warp;
-    bool active = env < a.nenv;
-    if (!active) env = a.nenv - 1;  // idle warps shadow the last env read-only and store nothing
+  // Work distribution: groups of `wpb` consecutive slots of the cost-sorted env order (heaviest
+  // first, api.cu:schedule_kernel) are handed out through an atomic counter, so the warps of a
+  // CTA own envs of similar cost (less waiting at the stage barriers) and light groups fill the
+  // tail.  Every warp of the CTA runs the same steps so that the CTA-wide barriers are uniform;
+  // the barriers keep the warps in the same code region, which is what makes the instruction
+  // cache work for this 400+ KB kernel (profiles/physics_r1.md).
+  __shared__ int s_group;
+  __shared__ __align__(8) unsigned long long hull_bar[8];
+  HullStage hs;
+  hs.buf = reinterpret_cast<float4*>(S + o.J); hs.cap = (m.maxcrow * o.ldj) / 4; hs.phase = 0; hs.resA = -1; hs.nA = 0;
+  hs.bar = (unsigned)__cvta_generic_to_shared(&hull_bar[warp]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs.bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+#define STAGE_SYNC(level) do { if ((a.sync_level & 7) >= (level) && attempt == 0) __syncthreads(); } while (0)
+  for (;;) {
+    if (threadIdx.x == 0) s_group = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    int slot = s_group * wpb + warp;
+    __syncthreads();
+    if (slot - warp >= a.nenv) break;
+    bool active = slot < a.nenv;
+    int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
+    int cost = 0;
     _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
     _Pragma("unroll 1") for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];
@@ -1572,7 +1661,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
     float time = a.time ? a.time[env] : 0.f;
     int nsteps = a.forward_only ? 1 : a.nsteps;
     for (int s = 0; s < nsteps; s++) {
-      FwdInfo fi = {0, 0, 0, 0};
+      FwdInfo fi = {0, 0, 0, 0, 0};
       // mj_checkPos / mj_checkVel, then forward; mj_checkAcc re-runs forward once from the reset state
       bool bad = active && (warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane));
       for (int attempt = 0; attempt < 2; attempt++) {
@@ -1582,12 +1671,12 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
           __syncwarp();
           flags |= 1;
         }
-        if (a.sync_level != 5) STAGE_SYNC(1);
+        STAGE_SYNC(1);
         if (active) kinematics(m, S, lane);
         STAGE_SYNC(2);
         if (active) crb_mass_matrix(m, S, lane);
         STAGE_SYNC(1);
-        if (active) collision(m, S, fi.ncon, flags, lane);
+        if (active) collision(m, S, fi.ncon, fi.nnarrow, flags, hs, lane);
         STAGE_SYNC(1);
         if (active) velocity_stage(m, S, lane);
         STAGE_SYNC(2);
@@ -1596,18 +1685,20 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (active) make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
         STAGE_SYNC(1);
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
-        if (active) {
-        copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
-        if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane); chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
-        else { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
-        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane);
-        _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
+        {
+        bool ssync = attempt == 0 && (a.sync_level & 8);
+        if (active) copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
+        if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane, active, ssync); if (active) chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+        else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
+        cost += 8 * fi.iter + fi.nnarrow;
+        if (active) _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();
         }
         bad = active && warp_bad(S + o.qacc, m.nv, lane);
         if (!bad) break;
       }
-      if (a.sync_level != 5 && a.sync_level >= 1 && a.sync_level < 3) __syncthreads();
+      if (a.sync_level & 7) __syncthreads();
       if (s == nsteps - 1 && active) {
         // observations of the state the step started from (same convention as mjData after mj_step)
         imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
@@ -1639,7 +1730,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
         __syncwarp();
       }
-      if (!a.forward_only && active) { integrate(m, S, lane); time += m.timestep; }
+      if (!a.forward_only) { integrate(m, S, lane, active, (a.sync_level & 8) != 0); time += m.timestep; }
     }
     if (!a.forward_only && active) {
       _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
@@ -1647,6 +1738,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
       if (a.time && lane == 0) a.time[env] = time;
     }
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
+    if (lane == 0 && active && !a.forward_only) a.cost[env] = cost;
     __syncwarp();
   }
 }

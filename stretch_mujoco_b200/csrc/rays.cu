@@ -476,10 +476,16 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
     }
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 32) {  // ordered compaction by warp 0 (ballot + popc keeps the geom-id order deterministic)
     int n = 0;
-    for (int k = 0; k < r.nraygeom; k++) if (flag[k]) list[n++] = k;
-    nlist = n;
+    for (int base = 0; base < r.nraygeom; base += 32) {
+      int k = base + tid;
+      bool keep = k < r.nraygeom && flag[k];
+      unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) list[n + __popc(mask & ((1u << tid) - 1))] = k;
+      n += __popc(mask);
+    }
+    if (tid == 0) nlist = n;
   }
   __syncthreads();
   int u = blockIdx.x * TILE + threadIdx.x, v = blockIdx.y * TILE + threadIdx.y;
