@@ -407,7 +407,7 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
 // `work` = this warp has a matrix to factor; `sync` = CTA-wide barrier in front of the 1100-instruction
 // straight-line factorisation so that all warps of the CTA stream it through the instruction cache
 // together (every warp of the CTA must then make this call, working or not).
-__device__ __noinline__ void build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, bool sync) {
+__device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, bool sync) {
   int nv = R.nv, ldj = R.ldj, ns = R.ns;
   float h[32];
   if (work) {
@@ -445,35 +445,36 @@ __device__ __noinline__ void build_hessian32(const Rows R, float* H, const float
       float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
       float iT = 1.0f / T;
       const float* Jc = R.J + (r - ns) * ldj;
-      __syncwarp();
-      // tmp_j = sum_k Hc[j,k] J_k with Hc[j,k] = sc_j sc_k * d2s/dU_j dU_k (exact cone Hessian)
+      // Exact cone Hessian in the scaled coordinates U (s = Dm/2 (N - mu T)^2):
+      //   Hc = Dm g g^T + c (I_t - u u^T),  g = (1, -mu u),  u = U_t / T,  c = -Dm mu (N - mu T) / T  (> 0)
+      // so J^T Hc J is dim+1 rank-1 updates: Dm vg vg^T - c vu vu^T + sum_j c sc_j^2 J_j J_j^T with
+      // vg = sum_j sc_j g_j J_j and vu = sum_{j>=1} sc_j u_j J_j.
+      float c = -Dm * mu * (N - mu * T) * iT;
+      float vg = mu * Jc[lane], vu = 0;
 #pragma unroll 1
-      for (int j = 0; j < dim; j++) {
-        float t = 0;
-#pragma unroll 1
-        for (int k = 0; k < dim; k++) {
-          float hjk;
-          if (j == 0 && k == 0) hjk = Dm;
-          else if (j == 0 || k == 0) hjk = -Dm * mu * U[j + k] * iT;
-          else hjk = Dm * (mu * N * U[j] * U[k] * iT * iT * iT - (j == k ? mu * (N - mu * T) * iT : 0.f));
-          t += hjk * sc[j] * sc[k] * Jc[k * ldj + lane];
-        }
-        tmpJ[j * ldj + lane] = t;   // lanes >= nv write the zero padding (J rows are zero padded)
+      for (int j = 1; j < dim; j++) {
+        float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + lane];
+        vu = fmaf(w, Jj, vu); vg = fmaf(-mu * w, Jj, vg);
       }
       __syncwarp();
+      tmpJ[lane] = vg; tmpJ[ldj + lane] = vu;   // lanes >= nv write the zero padding (J rows are zero padded)
+      __syncwarp();
+      rank1_row32(h, (lane < nv) ? Dm * vg : 0.f, tmpJ);
+      rank1_row32(h, (lane < nv) ? -c * vu : 0.f, tmpJ + ldj);
 #pragma unroll 1
-      for (int j = 0; j < dim; j++) rank1_row32(h, (lane < nv) ? Jc[j * ldj + lane] : 0.f, tmpJ + j * ldj);
+      for (int j = 1; j < dim; j++) rank1_row32(h, (lane < nv) ? c * sc[j] * sc[j] * Jc[j * ldj + lane] : 0.f, Jc + j * ldj);
       r += dim - 1;
     }
   }
   }
-  if (sync) __syncthreads();
+  bool any = sync ? (__syncthreads_or(work) != 0) : work;
   if (work) {
   chol_rows32(h, nv);
 #pragma unroll
   for (int k = 0; k < 32; k++) if (lane < nv && k <= lane) H[lane * ld + k] = h[k];
   __syncwarp();
   }
+  return any;
 }
 __device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane, bool work, bool sync) {
   Rows R;
@@ -1400,7 +1401,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   }
   int iter = 0;
   while (true) {
-    if (sync) { if (!__syncthreads_or(!done)) break; } else if (done) break;
+    if (!sync && done) break;
     if (!done) {
       mul_JT(R, qfc, force, lane);
       float g2 = 0;
@@ -1411,10 +1412,14 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
     }
     if (nv <= 32) {
-      build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane, !done, sync);
+      // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
+      // every warp whether any warp of the CTA is still iterating
+      if (!build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane, !done, sync)) break;
       if (!done) chol_solve32(S + o.H, search, nv, o.ldm, lane);
-    } else if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
-    if (sync) __syncthreads();
+    } else {
+      if (sync && !__syncthreads_or(!done)) break;
+      if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
+    }
     if (done) continue;
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
