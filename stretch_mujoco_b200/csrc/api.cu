@@ -410,6 +410,8 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs
   B->sync_level = 9;   // stage barriers (1) + CTA-uniform Newton loop (8), see physics.cu
   if (const char* e = getenv("SS_SYNC")) B->sync_level = atoi(e);
+  B->group_warps = 0;
+  if (const char* e = getenv("SS_GROUP")) B->group_warps = atoi(e);
   B->pack_bytes = (size_t)m.pk.nwords * 4;
   B->warps_per_block = wpb;
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
@@ -446,7 +448,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   StepArgs a;
   memset(&a, 0, sizeof(a));
   const ss_buffers& f = B->bufs;
-  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level;
+  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level; a.group_warps = B->group_warps;
   a.qpos = f.qpos; a.qvel = f.qvel; a.warm = f.qacc_warmstart; a.time = f.time; a.ctrl = f.ctrl;
   a.xpos = f.xpos; a.xquat = f.xquat; a.act_length = f.act_length; a.act_velocity = f.act_velocity;
   a.sensordata = f.sensordata; a.qacc = f.qacc; a.ncon = f.ncon; a.contact_geom = f.contact_geom;

@@ -30,7 +30,7 @@ struct ss_batch {
   ss_debug_buffers dbg;
   DevModel dm;  // model + this batch's buffer sizes and shared-memory layout
   size_t smem_per_env, pack_bytes;
-  int warps_per_block, grid, sync_level;
+  int warps_per_block, grid, sync_level, group_warps;
   long launches;
   int prev_nsteps = 1;
   int32_t *order = nullptr, *cost = nullptr, *work_counter = nullptr;  // cost-sorted env schedule (api.cu)

@@ -95,6 +95,25 @@ __device__ __forceinline__ void normalize3(float* a) {
   a[0] *= inv; a[1] *= inv; a[2] *= inv;
 }
 
+// Named barriers for a group of warps inside the CTA (bar = id | thread_count << 8; 0 = no barrier).
+__device__ __forceinline__ void group_sync(int bar) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar & 255), "r"(bar >> 8) : "memory");
+}
+__device__ __forceinline__ bool group_sync_or(int bar, bool pred) {
+  unsigned out, in = pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 p, %1, 0;\n"
+      "bar.red.or.pred q, %2, %3, p;\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(in), "r"(bar & 255), "r"(bar >> 8)
+      : "memory");
+  return out != 0;
+}
+
 // ----------------------------------------------------------------------------- dense algebra (single copies)
 // in-place Cholesky of the dense n x n matrix A (row stride ld, lower triangle) in shared memory.
 // Lane i owns row i (+32 for n > 32); left-looking so that only finished columns are read.
@@ -407,7 +426,7 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
 // `work` = this warp has a matrix to factor; `sync` = CTA-wide barrier in front of the 1100-instruction
 // straight-line factorisation so that all warps of the CTA stream it through the instruction cache
 // together (every warp of the CTA must then make this call, working or not).
-__device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, bool sync) {
+__device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, int sync) {
   int nv = R.nv, ldj = R.ldj, ns = R.ns;
   float h[32];
   if (work) {
@@ -467,7 +486,7 @@ __device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float
     }
   }
   }
-  bool any = sync ? (__syncthreads_or(work) != 0) : work;
+  bool any = sync ? group_sync_or(sync, work) : work;
   if (work) {
   chol_rows32(h, nv);
 #pragma unroll
@@ -476,7 +495,7 @@ __device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float
   }
   return any;
 }
-__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane, bool work, bool sync) {
+__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane, bool work, int sync) {
   Rows R;
   R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = 32;
   R.sd1 = R.sd2 = nullptr; R.info = nullptr; R.sc1 = R.sc2 = R.J = R.eD = R.eR = R.efl = R.con = nullptr;
@@ -632,9 +651,9 @@ struct Cvx {
   const float4* verts;
 };
 
-__device__ __noinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
-  float l[3], r[3] = {0, 0, 0};
-  matT_vec(l, g.mat, dir);
+// support point of an analytic primitive in its local frame (direction l, local)
+__device__ __forceinline__ void support_prim(const Cvx& g, const float* l, float* r) {
+  r[0] = r[1] = r[2] = 0;
   if (g.type == GEOM_SPHERE) {
     float n = sqrtf(dot3(l, l));
     if (n > MINVAL) { float s = g.size[0] / n; r[0] = l[0] * s; r[1] = l[1] * s; r[2] = l[2] * s; }
@@ -645,33 +664,67 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
     float n = sqrtf(l[0] * l[0] + l[1] * l[1]);
     if (n > MINVAL) { r[0] = l[0] / n * g.size[0]; r[1] = l[1] / n * g.size[0]; }
     r[2] = l[2] > 0 ? g.size[1] : -g.size[1];
-  } else if (g.type == GEOM_MESH) {
+  }
+}
+// warp arg-max over per-lane candidates (best, bi): lowest vertex index wins ties.  Two REDUX
+// instructions on an order-preserving integer image of the float instead of a 5-round shuffle butterfly.
+__device__ __forceinline__ int warp_argmax(float best, int bi) {
+  unsigned u = __float_as_uint(best);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  unsigned mx = __reduce_max_sync(FULL, u);
+  return (int)__reduce_min_sync(FULL, (u == mx) ? (unsigned)bi : 0x7fffffffu);
+}
+
+// support point of one convex geom in world coordinates (mesh hulls: lane-parallel vertex scan)
+__device__ __noinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
+  float l[3], r[3];
+  matT_vec(l, g.mat, dir);
+  if (g.type == GEOM_MESH) {
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
-#pragma unroll 8
+#pragma unroll 4
     for (int i = lane; i < g.nvert; i += 32) {
       float4 v = g.verts[i];
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
       if (s > best) { best = s; bi = i; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ob = __shfl_xor_sync(FULL, best, o); int oi = __shfl_xor_sync(FULL, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    float4 v = g.verts[bi];
+    float4 v = g.verts[warp_argmax(best, bi)];
     r[0] = v.x; r[1] = v.y; r[2] = v.z;
-  }
+  } else support_prim(g, l, r);
   mat_vec(out, g.mat, r);
   out[0] += g.pos[0]; out[1] += g.pos[1]; out[2] += g.pos[2];
 }
 
 struct Spt { float v[3], v1[3], v2[3]; };
 
+// Minkowski-difference support: both geoms are scanned in ONE loop so that the two vertex streams and
+// the two reductions overlap (the MPR iteration is a dependent chain of these calls).
 __device__ __noinline__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
-  float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  support(a, dir, s.v1, lane);
-  support(b, nd, s.v2, lane);
-  s.v[0] = s.v1[0] - s.v2[0]; s.v[1] = s.v1[1] - s.v2[1]; s.v[2] = s.v1[2] - s.v2[2];
+  float nd[3] = {-dir[0], -dir[1], -dir[2]}, la[3], lb[3], ra[3], rb[3];
+  matT_vec(la, a.mat, dir);
+  matT_vec(lb, b.mat, nd);
+  int na = a.type == GEOM_MESH ? a.nvert : 0, nb = b.type == GEOM_MESH ? b.nvert : 0;
+  float besta = -CUDART_INF_F, bestb = -CUDART_INF_F; int bia = 0x7fffffff, bib = 0x7fffffff;
+#pragma unroll 2
+  for (int i = lane; i < max(na, nb); i += 32) {
+    if (i < na) {
+      float4 v = a.verts[i];
+      float t = v.x * la[0] + v.y * la[1] + v.z * la[2];
+      if (t > besta) { besta = t; bia = i; }
+    }
+    if (i < nb) {
+      float4 v = b.verts[i];
+      float t = v.x * lb[0] + v.y * lb[1] + v.z * lb[2];
+      if (t > bestb) { bestb = t; bib = i; }
+    }
+  }
+  if (na) { float4 v = a.verts[warp_argmax(besta, bia)]; ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; }
+  else support_prim(a, la, ra);
+  if (nb) { float4 v = b.verts[warp_argmax(bestb, bib)]; rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; }
+  else support_prim(b, lb, rb);
+  mat_vec(s.v1, a.mat, ra);
+  mat_vec(s.v2, b.mat, rb);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.v1[k] += a.pos[k]; s.v2[k] += b.pos[k]; s.v[k] = s.v1[k] - s.v2[k]; }
 }
 
 #define MPR_TOL 1e-6f
@@ -1354,7 +1407,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
 // Every warp of the CTA makes this call (`active` = it owns an env).  With `sync` the Newton loop is
 // CTA-uniform: the warps meet before the gradient, the Hessian and the line search of every iteration
 // (converged warps only keep the barriers company), which lets them share instruction-cache lines.
-__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, bool sync) {
+__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, int sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv;
   float *qacc = S + o.qacc, *Ma = S + o.v_Ma, *grad = S + o.v_grad, *search = S + o.v_search, *mv = S + o.v_mv;
@@ -1417,7 +1470,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       if (!build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane, !done, sync)) break;
       if (!done) chol_solve32(S + o.H, search, nv, o.ldm, lane);
     } else {
-      if (sync && !__syncthreads_or(!done)) break;
+      if (sync && !group_sync_or(sync, !done)) break;
       if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
     }
     if (done) continue;
@@ -1479,7 +1532,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
 }
 
 // ----------------------------------------------------------------------------- S9: implicitfast + advance
-__device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane, bool active, bool sync) {
+__device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane, bool active, int sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv, ld = o.ldm;
   float h = m.timestep;
@@ -1638,7 +1691,11 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
   // tail.  Every warp of the CTA runs the same steps so that the CTA-wide barriers are uniform;
   // the barriers keep the warps in the same code region, which is what makes the instruction
   // cache work for this 400+ KB kernel (profiles/physics_r1.md).
-  __shared__ int s_group;
+  __shared__ int s_group[8];
+  // barrier groups: the CTA's warps are split into groups of a.group_warps that synchronise among
+  // themselves only (named barriers 1..), fetch work independently and overlap each other's waits
+  int gw = a.group_warps > 0 ? min(a.group_warps, wpb) : wpb, grp = warp / gw, w0 = grp * gw, nwg = min(gw, wpb - w0);
+  int bar = (1 + grp) | ((nwg * 32) << 8);
   __shared__ __align__(8) unsigned long long hull_bar[8];
   HullStage hs;
   hs.buf = reinterpret_cast<float4*>(S + o.J); hs.cap = (m.maxcrow * o.ldj) / 4; hs.phase = 0; hs.resA = -1; hs.nA = 0;
@@ -1648,13 +1705,13 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-#define STAGE_SYNC(level) do { if ((a.sync_level & 7) >= (level) && attempt == 0) __syncthreads(); } while (0)
+#define STAGE_SYNC(level) do { if ((a.sync_level & 7) >= (level) && attempt == 0) group_sync(bar); } while (0)
   for (;;) {
-    if (threadIdx.x == 0) s_group = atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    int slot = s_group * wpb + warp;
-    __syncthreads();
-    if (slot - warp >= a.nenv) break;
+    if (warp == w0 && lane == 0) s_group[grp] = atomicAdd(a.work_counter, nwg);
+    group_sync(bar);
+    int slot = s_group[grp] + (warp - w0);
+    group_sync(bar);
+    if (slot - (warp - w0) >= a.nenv) break;
     bool active = slot < a.nenv;
     int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
     int cost = 0;
@@ -1691,7 +1748,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         STAGE_SYNC(1);
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
         {
-        bool ssync = attempt == 0 && (a.sync_level & 8);
+        int ssync = (attempt == 0 && (a.sync_level & 8)) ? bar : 0;
         if (active) copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
         if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane, active, ssync); if (active) chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
@@ -1703,7 +1760,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         bad = active && warp_bad(S + o.qacc, m.nv, lane);
         if (!bad) break;
       }
-      if (a.sync_level & 7) __syncthreads();
+      if (a.sync_level & 7) group_sync(bar);
       if (s == nsteps - 1 && active) {
         // observations of the state the step started from (same convention as mjData after mj_step)
         imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
@@ -1735,7 +1792,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
         __syncwarp();
       }
-      if (!a.forward_only) { integrate(m, S, lane, active, (a.sync_level & 8) != 0); time += m.timestep; }
+      if (!a.forward_only) { integrate(m, S, lane, active, (a.sync_level & 8) ? bar : 0); time += m.timestep; }
     }
     if (!a.forward_only && active) {
       _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
