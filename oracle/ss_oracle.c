@@ -711,28 +711,34 @@ static void ls_eval(const om_model* m, const om_data* d, const double* jar, cons
   *p0 = c; *p1 = g; *p2 = h;
 }
 
-/* exact line search on the convex piecewise-smooth 1-D cost: safeguarded Newton on p'(a)=0 */
+/* exact line search on the convex piecewise-smooth 1-D cost: safeguarded Newton on p'(a)=0.
+   p' is monotone but jumps at the kinks of the constraint laws, so the minimiser can sit ON a kink where no
+   point has |p'| < gtol: the bracket [lo, hi] is then shrunk (Newton step if it stays inside, else secant,
+   bisection every other step so that the width at least halves) until it is numerically a point, and the
+   left end (p' < 0, guaranteed decrease) is returned. */
 static double line_search(const om_model* m, const om_data* d, const double* jar, const double* jv, double g1,
                           double g2, double gtol) {
-  double lo = 0, hi = -1, a = 0, p0, p1, p2, dlo, dhi = 0;
+  double lo = 0, hi = -1, a = 0, p0, p1, p2, dlo, dhi = 0, d0;
   ls_eval(m, d, jar, jv, g1, g2, 0, &p0, &p1, &p2);
   if (p1 >= 0 || p2 <= 0) return 0;
-  dlo = p1;
+  dlo = d0 = p1;
   a = -p1 / p2;
-  for (int it = 0; it < m->ls_iterations; it++) {
+  int niter = m->ls_iterations > 100 ? m->ls_iterations : 100;
+  for (int it = 0; it < niter; it++) {
     ls_eval(m, d, jar, jv, g1, g2, a, &p0, &p1, &p2);
-    if (fabs(p1) < gtol) return a;
+    if (fabs(p1) < gtol || fabs(p1) <= 1e-14 * fabs(d0)) return a;
     if (p1 < 0) { lo = a; dlo = p1; } else { hi = a; dhi = p1; }
+    if (hi > 0 && hi - lo <= 4e-16 * hi) return lo > 0 ? lo : a;
     double an = (p2 > 0) ? a - p1 / p2 : -1;
     if (hi < 0) {
       if (!(an > lo)) an = 2 * a + 1e-12;
-    } else if (!(an > lo && an < hi)) {
-      an = lo + (hi - lo) * (-dlo) / (dhi - dlo);   /* secant on the monotone derivative */
-      if (!(an > lo && an < hi)) an = 0.5 * (lo + hi);
+    } else if (!(an > lo && an < hi) || (it & 1)) {
+      double sec = lo + (hi - lo) * (-dlo) / (dhi - dlo);   /* secant on the monotone derivative */
+      an = ((it & 1) || !(sec > lo && sec < hi)) ? 0.5 * (lo + hi) : sec;
     }
     a = an;
   }
-  return a;
+  return lo > 0 ? lo : a;
 }
 
 /* grad = M qacc - qfrc_smooth - J^T force; also refreshes qfrc_constraint. Returns |grad|. */

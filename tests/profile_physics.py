@@ -18,3 +18,5 @@ for p in range(3):
 B.ctrl.copy_(bench.ctrl_torch(0, 0, nenv, 3, lo, hi, dev)); B.step(nsteps)
 torch.cuda.synchronize()
 print("iters mean", B.solver_iter.float().mean().item(), "ncon mean", B.ncon.float().mean().item(), "max", B.ncon.max().item(), "flags", B.env_flags.max().item())
+it = B.solver_iter.cpu().numpy(); print("iter hist", np.bincount(it, minlength=12)[:16].tolist())
+g = it[: (len(it) // 7) * 7].reshape(-1, 7); print("mean", it.mean(), "mean of max-of-7 (env order)", g.max(1).mean())
