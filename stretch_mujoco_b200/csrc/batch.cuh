@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct StepArgs {
-  int nenv, nsteps, forward_only, sync_level, group_warps, trace_env;
+  int nenv, nsteps, forward_only, sync_level, group_warps;
   float *qpos, *qvel, *warm, *time, *ctrl;
   float *xpos, *xquat, *act_length, *act_velocity, *sensordata, *qacc;
   int32_t *ncon, *contact_geom;

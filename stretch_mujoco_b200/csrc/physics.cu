@@ -17,7 +17,6 @@
 #include "model.cuh"
 #include "batch.cuh"
 #include <math_constants.h>
-#include <cstdio>
 
 #define FULL 0xffffffffu
 #define MINVAL 1e-15f
@@ -1408,7 +1407,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
 // Every warp of the CTA makes this call (`active` = it owns an env).  With `sync` the Newton loop is
 // CTA-uniform: the warps meet before the gradient, the Hessian and the line search of every iteration
 // (converged warps only keep the barriers company), which lets them share instruction-cache lines.
-__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, int sync, int sync_dbg, bool trace) {
+__device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, int sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv;
   float *qacc = S + o.qacc, *Ma = S + o.v_Ma, *grad = S + o.v_grad, *search = S + o.v_search, *mv = S + o.v_mv;
@@ -1445,7 +1444,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   __syncwarp();
   eval_constraints<false>(R, 1.0f, cs, dg, dh, lane);
   cost = cw;
-  if (trace && lane == 0) printf("[trace] nefc %d ns %d ncon %d cost_warm %.9g cost_smooth %.9g scale %g tol %g\n", nefc, ns, ncon, cw, cs, scale, m.tolerance);
   if (!(cw <= cs)) {  // also catches NaN warm starts
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
@@ -1463,7 +1461,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
       g2 = warp_sum(g2);
       __syncwarp();
-      if (trace && lane == 0) printf("[trace] iter %d cost %.9g |grad| %.6g\n", iter, cost, sqrtf(g2));
       if (iter >= m.iterations) done = true;
       else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
     }
@@ -1481,7 +1478,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     float gs = 0, ss = 0;
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { gs += grad[i] * search[i]; ss += search[i] * search[i]; }
     gs = warp_sum(gs); ss = warp_sum(ss);
-    if (trace && lane == 0) printf("[trace]   gs %.6g ss %.6g expected-decrease*scale %.3g\n", gs, ss, scale * 0.5f * (-gs));
     if (!(gs < 0) || scale * 0.5f * (-gs) < m.tolerance) { done = true; continue; }
     symv(mv, M, search, nv, o.ldm, lane);
     mul_J(R, jv, search, lane);
@@ -1493,7 +1489,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     float p0, p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
     eval_constraints<false>(R, 0.f, p0, p1, p2, lane);
     p1 += q1; p2 += q2;
-    if (trace && lane == 0) printf("[trace]   ls p1(0) %.6g p2(0) %.6g q1 %.6g q2 %.6g\n", p1, p2, q1, q2);
     if (!(p1 < 0) || !(p2 > 0)) { done = true; continue; }
     float d0 = p1;
     dlo = p1;
@@ -1515,7 +1510,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       }
       a = an;
     }
-    if (trace && lane == 0) printf("[trace]   alpha %.6g p1(alpha) %.6g gtol %.3g\n", a, p1, gtol);
     if (!(a > 0)) { done = true; continue; }
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
@@ -1528,9 +1522,8 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       cost += warp_sum(gsum);
     }
     iter++;
-    if (trace && lane == 0) printf("[trace]   new cost %.9g improvement %.6g thresh %.3g\n", cost, oldcost - cost, fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost)));
     // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
-    if (!(sync_dbg & 16) && oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
+    if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
       mul_JT(R, qfc, force, lane);
       done = true;
     }
@@ -1759,7 +1752,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (active) copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
         if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane, active, ssync); if (active) chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
-        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync, a.sync_level, active && env == a.trace_env);
+        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
         cost += 8 * fi.iter + fi.nnarrow;
         if (active) _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();

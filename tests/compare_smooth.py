@@ -42,3 +42,16 @@ for e in np.argsort(-err)[:4]:
     print("  qvel", v[e, 16:23])
     # residual of the device's answer in fp64: M qacc - qfs - qfc
     r = o["M"][e] @ qa[e].astype(np.float64) - ofs[e] - qfc[e]; print("  residual(gpu qacc, true M, gpu qfc)", r[16:23])
+print("=== contacts of outlier envs")
+o3 = om.forward(q, v, c, w, want=("ncon", "contact_geom", "contact_dist", "contact_pos", "contact_frame"))
+gd = B.contact_dist.cpu().numpy(); gp = B.dbg["contact_pos"].cpu().numpy(); gnrm = B.dbg["contact_normal"].cpu().numpy(); gg = B.contact_geom.cpu().numpy()
+gnames = _[2] if False else None
+for e in np.argsort(-err)[:5]:
+    n = int(o3["ncon"][e])
+    print("env", e, "err %.2e" % err[e], "ncon", n)
+    for k in range(n):
+        print("   geoms", gg[e, k], o3["contact_geom"][e, k], "dist gpu %.7f orcl %.7f" % (gd[e, k], o3["contact_dist"][e, k]),
+              "| dpos %.2e" % np.abs(gp[e, k] - o3["contact_pos"][e, k]).max(), "| normal gpu", gnrm[e, k].round(5), "orcl", o3["contact_frame"][e, k].round(5))
+# global contact statistics
+nc = o3["ncon"]; m_ = np.arange(gd.shape[1])[None, :] < nc[:, None]
+dd = np.abs(gd[:, :o3["contact_dist"].shape[1]] - o3["contact_dist"][:, :gd.shape[1]])[m_[:, :o3["contact_dist"].shape[1]]] if gd.shape[1] <= o3["contact_dist"].shape[1] else None
