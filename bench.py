@@ -135,7 +135,7 @@ def run_reference(args):
     timed = rates[args.warmup:]
     total_t = float((nenv * MJ_STEPS_PER_STEP / timed).sum())
     value = nenv * MJ_STEPS_PER_STEP * len(timed) / total_t
-    sample = f"{nenv} envs x {MJ_STEPS_PER_STEP} mj_steps per step (bounded sample of the 4096-env workload)"
+    sample = f"{nenv} envs x {MJ_STEPS_PER_STEP} mj_steps per step, {args.steps} timed steps of the same ctrl stream"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(timed),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -252,6 +252,13 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "physics_traffic.json")))
+        if nenv == 4096:
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+    except Exception:
+        pass
     achieved = ALGO_BYTES_PER_ENV_STEP * nenv * MJ_STEPS_PER_STEP / (kernel_ms * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -266,16 +273,18 @@ def run_ours(args):
                     "d2h_bytes_per_step": nenv * 24 * 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "ss_physics_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "ss_physics_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * nenv * MJ_STEPS_PER_STEP,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "note": "physics is issue/latency bound, not HBM bound: 828 algorithmic B per env-step "
-                                 "(SURVEY.md 8(d)); see profiles/ for issue-slot utilisation"},
+                         "note": "physics is instruction-issue/latency bound, not HBM bound: 828 algorithmic B per env-step "
+                                 "(SURVEY.md 8(d)); measured DRAM traffic is below that because the state stays in shared "
+                                 "memory for the 50 steps of a launch; see profiles/physics_r1.md"},
             "rollout_metrics": {"env_steps": float(gathered[:, 0].sum()), "sum_abs_qpos": float(gathered[:, 2].sum()),
                                 "contacts_last_step": float(gathered[:, 3].sum()), "envs_reset": float(gathered[:, 4].sum())}}
     if world == 1 and not args.no_cpu:
-        rates, cores, _ = cpu_sample(args.cpu_nenv, MJ_STEPS_PER_STEP, 4)
+        rates, cores, _ = cpu_sample(args.cpu_nenv, MJ_STEPS_PER_STEP, 11)
         line["cpu_baseline"] = {"value": float(np.median(rates[1:])), "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_nenv} envs x {MJ_STEPS_PER_STEP} mj_steps x 3 periods of the same ctrl stream",
+                                "sample": f"{args.cpu_nenv} envs x {MJ_STEPS_PER_STEP} mj_steps x 10 periods of the same ctrl stream (median period)",
                                 "note": "CPU restatement of the mujoco==3.2.6 mj_step path (oracle/), not the MuJoCo binary"}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -289,7 +298,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nenv", type=int, default=4096)
-    ap.add_argument("--cpu-nenv", type=int, default=256)
+    ap.add_argument("--cpu-nenv", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
