@@ -103,7 +103,7 @@ static int build_layout(DevModel& m) {
   int off = 0;
   auto take = [&](int n) { int r = off; off += (n + 3) & ~3; return r; };
   int nv = m.nv, nb = m.nbody;
-  o.ldm = nv | 1;
+  o.ldm = nv <= 32 ? ((nv + 3) & ~3) : (nv | 1);   // n <= 32: float4 rows (register Cholesky path); else odd stride (scalar, conflict-free)
   o.ldj = (nv + 3) & ~3;   // 16-byte aligned rows (float4 operand loads in the Hessian build)
   // live for the whole step
   o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv); o.qacc = take(nv);

@@ -165,66 +165,89 @@ __device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld,
   }
 }
 
-// y = A x for the symmetric dense matrix in shared memory (full storage)
+// y = A x for the symmetric dense matrix in shared memory (full storage).  Row stride a multiple of 4
+// (the n <= 32 layout): lane i reads row i and x as float4 (conflict-free: 7 * lane mod 8 is a
+// permutation), the tail below n scalar.
 __device__ __noinline__ void symv(float* y, const float* A, const float* x, int n, int ld, int lane) {
   _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
     float s = 0;
     const float* r = A + i * ld;
-    for (int k = 0; k < n; k++) s += r[k] * x[k];
+    int k = 0;
+    if ((ld & 3) == 0) {
+      const float4 *r4 = reinterpret_cast<const float4*>(r), *x4 = reinterpret_cast<const float4*>(x);
+      for (; k + 4 <= n; k += 4) {
+        float4 a = r4[k >> 2], b = x4[k >> 2];
+        s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+    }
+    for (; k < n; k++) s += r[k] * x[k];
     y[i] = s;
   }
   __syncwarp();
 }
 
-// copy the lower triangle of src into dst (row stride ld)
-__device__ __noinline__ void copy_lower(float* dst, const float* src, int n, int ld, int lane) {
-  _Pragma("unroll 1") for (int i = lane; i < n; i += 32)
-    for (int k = 0; k <= i; k++) dst[i * ld + k] = src[i * ld + k];
+// dst = src for a whole n x ld matrix (ld a multiple of 4: float4 copy) or its lower triangle (odd ld)
+__device__ __noinline__ void copy_matrix(float* dst, const float* src, int n, int ld, int lane) {
+  if ((ld & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    _Pragma("unroll 1") for (int i = lane; i < (n * ld) >> 2; i += 32) d4[i] = s4[i];
+  } else {
+    _Pragma("unroll 1") for (int i = lane; i < n; i += 32)
+      for (int k = 0; k <= i; k++) dst[i * ld + k] = src[i * ld + k];
+  }
   __syncwarp();
 }
 
 // ---- n <= 32: one matrix row per lane held in REGISTERS, columns exchanged by warp shuffles ------------
-// Right-looking Cholesky on a register row a[0..31] (lane i = row i; entries k > i are don't-care).
-// 2 instructions per (row, column) pair, no shared-memory traffic and no dependent-load chains.
-__device__ __forceinline__ void chol_rows32(float (&a)[32], int n) {
-#pragma unroll
-  for (int j = 0; j < 32; j++) {  // rows >= n are identity rows: no guard, straight-line convergent code
-    float piv = __shfl_sync(FULL, a[j], j);
-    float l = a[j] * rsqrtf(fmaxf(piv, MINVAL));
-    a[j] = l;
-#pragma unroll
-    for (int k = j + 1; k < 32; k++) a[k] = fmaf(-l, __shfl_sync(FULL, l, k), a[k]);
-  }
-  (void)n;
-}
-// a += s * v[0..31] (v in shared memory, 16-byte aligned, zero padded to 32)
-__device__ __forceinline__ void rank1_row32(float (&a)[32], float s, const float* v) {
+// a += s * v[0..NT) (v in shared memory, 16-byte aligned)
+template <int NT>
+__device__ __forceinline__ void rank1_row(float (&a)[NT], float s, const float* v) {
   const float4* v4 = reinterpret_cast<const float4*>(v);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
+  for (int k = 0; k < NT / 4; k++) {
     float4 t = v4[k];
     a[4 * k] = fmaf(s, t.x, a[4 * k]); a[4 * k + 1] = fmaf(s, t.y, a[4 * k + 1]);
     a[4 * k + 2] = fmaf(s, t.z, a[4 * k + 2]); a[4 * k + 3] = fmaf(s, t.w, a[4 * k + 3]);
   }
 }
-// solve L L^T x = b in place (x in shared memory, L static in shared memory, running value in a register)
-__device__ __noinline__ void chol_solve32(const float* L, float* xs, int n, int ld, int lane) {
-  bool in = lane < n;
-  float x = in ? xs[lane] : 0.f, dinv = in ? 1.0f / L[lane * ld + lane] : 0.f;
-  const float* Lr = L + lane * ld;
-#pragma unroll 4
-  for (int j = 0; j < n; j++) {
-    float lij = (in && lane > j) ? Lr[j] : 0.f;
-    float xj = __shfl_sync(FULL, x * dinv, j);
-    x = (lane == j) ? xj : fmaf(-lij, xj, x);
+// Right-looking Cholesky of the register rows a[0..NT) (lane i = row i; entries k > i are don't-care,
+// rows >= n are identity rows, lanes >= NT idle) FUSED with the solve of L L^T x = b:
+//  * forward substitution rides along the factorisation (y_j is final once column j is scaled);
+//  * L is then parked in shared memory (row stride ld, float4 stores) and the backward substitution reads
+//    row j across the lanes (one conflict-free load per column, all issued up front).
+// 2 instructions per (row, column) pair + ~11 per column; straight-line convergent code.
+template <int NT>
+__device__ __forceinline__ void chol_solve_rows(float (&a)[NT], float* Ls, int n, int ld, float* xs, int lane) {
+  float x = lane < n ? xs[lane] : 0.f, rinv_own = 1.f;
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    float piv = __shfl_sync(FULL, a[j], j);
+    float rinv = rsqrtf(fmaxf(piv, MINVAL));
+    float l = a[j] * rinv;
+    a[j] = l;
+    float yj = __shfl_sync(FULL, x, j) * rinv;
+    if (lane == j) { rinv_own = rinv; x = yj; }
+    if (lane > j) x = fmaf(-l, yj, x);
+#pragma unroll
+    for (int k = j + 1; k < NT; k++) a[k] = fmaf(-l, __shfl_sync(FULL, l, k), a[k]);
   }
-#pragma unroll 4
-  for (int j = n - 1; j >= 0; j--) {
-    float lji = (lane < j) ? L[j * ld + lane] : 0.f;
-    float xj = __shfl_sync(FULL, x * dinv, j);
-    x = (lane == j) ? xj : fmaf(-lji, xj, x);
+  if (lane < n) {
+    float4* L4 = reinterpret_cast<float4*>(Ls + lane * ld);
+#pragma unroll
+    for (int k = 0; k < NT / 4; k++)
+      if (4 * k < ld) L4[k] = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
   }
-  if (in) xs[lane] = x;
+  __syncwarp();
+  float lj[NT];
+#pragma unroll
+  for (int j = 0; j < NT; j++) lj[j] = (j < n && lane < j) ? Ls[j * ld + lane] : 0.f;
+#pragma unroll
+  for (int j = NT - 1; j >= 0; j--) {
+    float xj = __shfl_sync(FULL, x * rinv_own, j);
+    x = (lane == j) ? xj : fmaf(-lj[j], xj, x);
+  }
+  if (lane < n) xs[lane] = x;
   __syncwarp();
 }
 
@@ -420,21 +443,22 @@ __device__ __noinline__ void build_hessian(const Rows R, float* H, const float* 
 }
 
 // n <= 32 variant: the sparse rows are folded into a shared-memory copy of M, then lane i pulls row i
-// into registers, accumulates the dense contact rows as rank-1 updates (one unrolled body shared by
-// quadratic rows and cone blocks), factors in registers and writes only the factor L back.
-// With R.nefc == 0 this is a plain Cholesky factorisation of M into H (H may alias M).
-// `work` = this warp has a matrix to factor; `sync` = CTA-wide barrier in front of the 1100-instruction
-// straight-line factorisation so that all warps of the CTA stream it through the instruction cache
-// together (every warp of the CTA must then make this call, working or not).
-__device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane, bool work, int sync) {
+// into registers (float4 loads), accumulates the dense contact rows as rank-1 updates (one unrolled body
+// shared by quadratic rows and cone blocks), factors in registers and solves H x = b for the vector xs in
+// place (chol_solve_rows).  With R.nefc == 0 this is a plain Cholesky solve with M (H may alias M).
+// `alive` = this warp is still iterating (vote returned to the caller); `work` = it has a system to solve;
+// `sync` = barrier in front of the ~1000-instruction straight-line factorisation so that all warps of the
+// group stream it through the instruction cache together (every warp of the group must then make this
+// call, working or not).
+template <int NT>
+__device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* M, float* tmpJ, int ld, float* xs, int lane,
+                                           bool alive, bool work, int sync) {
   int nv = R.nv, ldj = R.ldj, ns = R.ns;
-  float h[32];
+  float h[NT];
   if (work) {
+  if (H != M) copy_matrix(H, M, nv, ld, lane);
   if (lane < nv) {
     float* Hi = H + lane * ld;
-    const float* Mi = M + lane * ld;
-#pragma unroll 1
-    for (int k = 0; k <= lane; k++) Hi[k] = Mi[k];
 #pragma unroll 1
     for (int r = 0; r < ns; r++) {
       if (INFO_STATE(R.info[r]) != ST_QUADRATIC) continue;
@@ -446,14 +470,24 @@ __device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float
     }
   }
   __syncwarp();
+  {
+    const float4* H4 = reinterpret_cast<const float4*>(H + min(lane, nv - 1) * ld);
 #pragma unroll
-  for (int k = 0; k < 32; k++) h[k] = (lane < nv && k <= lane) ? H[lane * ld + k] : ((k == lane) ? 1.f : 0.f);
+    for (int k = 0; k < NT / 4; k++) {
+      float4 t = (4 * k < ld) ? H4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+      h[4 * k] = t.x; h[4 * k + 1] = t.y; h[4 * k + 2] = t.z; h[4 * k + 3] = t.w;
+    }
+    if (lane >= nv) {
+#pragma unroll
+      for (int k = 0; k < NT; k++) h[k] = (k == lane) ? 1.f : 0.f;
+    }
+  }
 #pragma unroll 1
   for (int r = ns; r < R.nefc; r++) {
     int inf = R.info[r], st = INFO_STATE(inf);
     if (st == ST_QUADRATIC) {
       const float* Jr = R.J + (r - ns) * ldj;
-      rank1_row32(h, (lane < nv) ? R.eD[r] * Jr[lane] : 0.f, Jr);
+      rank1_row<NT>(h, (lane < nv) ? R.eD[r] * Jr[lane] : 0.f, Jr);
     } else if (st == ST_CONE) {
       const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
       int dim = __float_as_int(con[C_DIM]);
@@ -469,38 +503,41 @@ __device__ __noinline__ bool build_hessian32(const Rows R, float* H, const float
       // so J^T Hc J is dim+1 rank-1 updates: Dm vg vg^T - c vu vu^T + sum_j c sc_j^2 J_j J_j^T with
       // vg = sum_j sc_j g_j J_j and vu = sum_{j>=1} sc_j u_j J_j.
       float c = -Dm * mu * (N - mu * T) * iT;
-      float vg = mu * Jc[lane], vu = 0;
+      int jl = min(lane, ldj - 1);
+      float vg = mu * Jc[jl], vu = 0;
 #pragma unroll 1
       for (int j = 1; j < dim; j++) {
-        float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + lane];
+        float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + jl];
         vu = fmaf(w, Jj, vu); vg = fmaf(-mu * w, Jj, vg);
       }
       __syncwarp();
-      tmpJ[lane] = vg; tmpJ[ldj + lane] = vu;   // lanes >= nv write the zero padding (J rows are zero padded)
+      if (lane < ldj) { tmpJ[lane] = lane < nv ? vg : 0.f; tmpJ[ldj + lane] = lane < nv ? vu : 0.f; }
       __syncwarp();
-      rank1_row32(h, (lane < nv) ? Dm * vg : 0.f, tmpJ);
-      rank1_row32(h, (lane < nv) ? -c * vu : 0.f, tmpJ + ldj);
+      rank1_row<NT>(h, (lane < nv) ? Dm * vg : 0.f, tmpJ);
+      rank1_row<NT>(h, (lane < nv) ? -c * vu : 0.f, tmpJ + ldj);
 #pragma unroll 1
-      for (int j = 1; j < dim; j++) rank1_row32(h, (lane < nv) ? c * sc[j] * sc[j] * Jc[j * ldj + lane] : 0.f, Jc + j * ldj);
+      for (int j = 1; j < dim; j++) rank1_row<NT>(h, (lane < nv) ? c * sc[j] * sc[j] * Jc[j * ldj + jl] : 0.f, Jc + j * ldj);
       r += dim - 1;
     }
   }
   }
-  bool any = sync ? group_sync_or(sync, work) : work;
-  if (work) {
-  chol_rows32(h, nv);
-#pragma unroll
-  for (int k = 0; k < 32; k++) if (lane < nv && k <= lane) H[lane * ld + k] = h[k];
-  __syncwarp();
-  }
+  bool any = sync ? group_sync_or(sync, alive) : alive;
+  if (work) chol_solve_rows<NT>(h, H, nv, ld, xs, lane);
   return any;
 }
-__device__ __forceinline__ void chol_factor32(float* A, int n, int ld, int lane, bool work, int sync) {
+// dispatch on the register tile (28 columns cover the Stretch robot's nv = 26 with 24 % fewer pair updates)
+__device__ __forceinline__ bool hessian_solve32(const Rows& R, float* H, const float* M, float* tmpJ, int ld, float* xs, int lane,
+                                                bool alive, bool work, int sync) {
+  if (R.nv <= 28 && R.ldj <= 28) return hessian_solve<28>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
+  return hessian_solve<32>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
+}
+// x = A^-1 b for an SPD matrix in shared memory (factor left in A)
+__device__ __forceinline__ void chol_solve32(float* A, int n, int ld, float* xs, int lane, bool work, int sync) {
   Rows R;
-  R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = 32;
+  R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = (n + 3) & ~3;
   R.sd1 = R.sd2 = nullptr; R.info = nullptr; R.sc1 = R.sc2 = R.J = R.eD = R.eR = R.efl = R.con = nullptr;
   R.jar = R.jv = R.force = nullptr; R.ncon = 0;
-  build_hessian32(R, A, A, nullptr, ld, lane, work, sync);
+  hessian_solve32(R, A, A, nullptr, ld, xs, lane, work, work, sync);
 }
 
 // ----------------------------------------------------------------------------- S1: kinematics + inertias + dof axes
@@ -646,7 +683,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
 
 // ----------------------------------------------------------------------------- S1c: collision
 struct Cvx {
-  int type, nvert, mesh;
+  int type, nvert, mesh, soff;   // soff: float4 index of the staged hull in shared memory, -1 = not staged
   float pos[3], mat[9], size[3];
   const float4* verts;
 };
@@ -676,7 +713,7 @@ __device__ __forceinline__ int warp_argmax(float best, int bi) {
 }
 
 // support point of one convex geom in world coordinates (mesh hulls: lane-parallel vertex scan)
-__device__ __noinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
+__device__ __forceinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
   float l[3], r[3];
   matT_vec(l, g.mat, dir);
   if (g.type == GEOM_MESH) {
@@ -697,30 +734,38 @@ __device__ __noinline__ void support(const Cvx& g, const float* dir, float* out,
 struct Spt { float v[3], v1[3], v2[3]; };
 
 // Minkowski-difference support: both geoms are scanned in ONE loop so that the two vertex streams and
-// the two reductions overlap (the MPR iteration is a dependent chain of these calls).
-__device__ __noinline__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
-  float nd[3] = {-dir[0], -dir[1], -dir[2]}, la[3], lb[3], ra[3], rb[3];
-  matT_vec(la, a.mat, dir);
-  matT_vec(lb, b.mat, nd);
-  int na = a.type == GEOM_MESH ? a.nvert : 0, nb = b.type == GEOM_MESH ? b.nvert : 0;
+// the two reductions overlap (the MPR iteration is a dependent chain of these calls).  SH = every mesh
+// operand is staged in shared memory (stage_pair): vertices come through LDS instead of generic loads.
+template <bool SH>
+__device__ __forceinline__ void msupport_scan(const Cvx& a, const Cvx& b, int na, int nb, const float* la, const float* lb, float* ra,
+                                              float* rb, int lane) {
+  const float4* sm4 = reinterpret_cast<const float4*>(smem);
   float besta = -CUDART_INF_F, bestb = -CUDART_INF_F; int bia = 0x7fffffff, bib = 0x7fffffff;
 #pragma unroll 2
   for (int i = lane; i < max(na, nb); i += 32) {
     if (i < na) {
-      float4 v = a.verts[i];
+      float4 v = SH ? sm4[a.soff + i] : a.verts[i];
       float t = v.x * la[0] + v.y * la[1] + v.z * la[2];
       if (t > besta) { besta = t; bia = i; }
     }
     if (i < nb) {
-      float4 v = b.verts[i];
+      float4 v = SH ? sm4[b.soff + i] : b.verts[i];
       float t = v.x * lb[0] + v.y * lb[1] + v.z * lb[2];
       if (t > bestb) { bestb = t; bib = i; }
     }
   }
-  if (na) { float4 v = a.verts[warp_argmax(besta, bia)]; ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; }
-  else support_prim(a, la, ra);
-  if (nb) { float4 v = b.verts[warp_argmax(bestb, bib)]; rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; }
-  else support_prim(b, lb, rb);
+  if (na) { int k = warp_argmax(besta, bia); float4 v = SH ? sm4[a.soff + k] : a.verts[k]; ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; }
+  if (nb) { int k = warp_argmax(bestb, bib); float4 v = SH ? sm4[b.soff + k] : b.verts[k]; rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; }
+}
+__device__ __forceinline__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
+  float nd[3] = {-dir[0], -dir[1], -dir[2]}, la[3], lb[3], ra[3], rb[3];
+  matT_vec(la, a.mat, dir);
+  matT_vec(lb, b.mat, nd);
+  int na = a.type == GEOM_MESH ? a.nvert : 0, nb = b.type == GEOM_MESH ? b.nvert : 0;
+  if ((na == 0 || a.soff >= 0) && (nb == 0 || b.soff >= 0)) msupport_scan<true>(a, b, na, nb, la, lb, ra, rb, lane);
+  else msupport_scan<false>(a, b, na, nb, la, lb, ra, rb, lane);
+  if (!na) support_prim(a, la, ra);
+  if (!nb) support_prim(b, lb, rb);
   mat_vec(s.v1, a.mat, ra);
   mat_vec(s.v2, b.mat, rb);
 #pragma unroll
@@ -751,7 +796,7 @@ __device__ __forceinline__ bool reach_tolerance(const Spt* p, const Spt& v4, con
   float m1 = dv4 - dot3(p[1].v, dir), m2 = dv4 - dot3(p[2].v, dir), m3 = dv4 - dot3(p[3].v, dir);
   return fminf(fminf(m1, m2), m3) <= MPR_TOL;
 }
-__device__ __noinline__ float origin_tri_dist2(const float* a, const float* b, const float* c, float* w) {
+__device__ __forceinline__ float origin_tri_dist2(const float* a, const float* b, const float* c, float* w) {
   float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
   float ap[3] = {-a[0], -a[1], -a[2]};
   float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
@@ -784,7 +829,7 @@ __device__ __noinline__ float origin_tri_dist2(const float* a, const float* b, c
   w[0] = a[0] + ab[0] * v + ac[0] * u; w[1] = a[1] + ab[1] * v + ac[1] * u; w[2] = a[2] + ab[2] * v + ac[2] * u;
   return dot3(w, w);
 }
-__device__ __noinline__ void find_pos(const Spt* p, float* pos) {
+__device__ __forceinline__ void find_pos(const Spt* p, float* pos) {
   float dir[3], b[4], t[3], sum;
   portal_dir(p, dir);
   cross3(t, p[1].v, p[2].v); b[0] = dot3(t, p[3].v);
@@ -809,7 +854,7 @@ __device__ __noinline__ void find_pos(const Spt* p, float* pos) {
 
 // Minkowski Portal Refinement; warp-uniform control flow, mesh support is lane-parallel.
 // One support call site (phase machine) keeps the code small.
-__device__ __noinline__ bool mpr_penetration(const Cvx& A, const Cvx& B, float* depth, float* dir_out, float* pos, int lane) {
+__device__ __forceinline__ bool mpr_penetration(const Cvx& A, const Cvx& B, float* depth, float* dir_out, float* pos, int lane) {
   Spt p[4], v4;
   float dir[3], va[3], vb[3];
   for (int k = 0; k < 3; k++) { p[0].v[k] = A.pos[k] - B.pos[k]; p[0].v1[k] = A.pos[k]; p[0].v2[k] = B.pos[k]; }
@@ -890,7 +935,7 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
   quat_normalize(q);
   quat2mat(c.mat, q);
   c.size[0] = PKF(cg_size)[3 * cg]; c.size[1] = PKF(cg_size)[3 * cg + 1]; c.size[2] = PKF(cg_size)[3 * cg + 2];
-  c.verts = nullptr; c.nvert = 0; c.mesh = -1;
+  c.verts = nullptr; c.nvert = 0; c.mesh = -1; c.soff = -1;
   if (c.type == GEOM_MESH) {
     int mid = PKI(cg_dataid)[cg];
     c.verts = m.hull_vert + PKI(mesh_hulladr)[mid]; c.nvert = PKI(mesh_hullnum)[mid]; c.mesh = mid;
@@ -900,7 +945,7 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
 struct ContactOut { float dist[4], pos[4][3], n[3]; int count; };
 
 // analytic plane-vs-primitive routines and MPR for the rest; fills up to 4 contacts
-__device__ __noinline__ void narrow_pair(const Cvx& A, const Cvx& B, float margin, ContactOut& out, int lane) {
+__device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, float margin, ContactOut& out, int lane) {
   out.count = 0;
   if (A.type == GEOM_PLANE) {
     float n[3] = {A.mat[2], A.mat[5], A.mat[8]};
@@ -981,12 +1026,21 @@ __device__ __noinline__ void narrow_pair(const Cvx& A, const Cvx& B, float margi
   }
 }
 
+// Single noinline body of the narrowphase; the operands are copied into registers once (they arrive through
+// local memory) and everything below (MPR, support scans) is inlined so that they stay there.
+__device__ __noinline__ void narrow_pair(const Cvx& A_, const Cvx& B_, float margin, ContactOut& out_, int lane) {
+  const Cvx A = A_, B = B_;
+  ContactOut out;
+  narrow_pair_body(A, B, margin, out, lane);
+  out_ = out;
+}
+
 // Hull staging: MPR calls the support function of both hulls 20-60 times per query, each call a
 // scan over all hull vertices.  Instead of scanning them in global memory (L2 latency per call; the
 // L1 is carved down to ~30 KB by the shared-memory working sets) the pair's hulls are pulled once
 // into the env's not-yet-used Jacobian region by TMA bulk copies that complete on a per-warp
 // mbarrier.  Slot A (offset 0) is reused while consecutive pairs share their first geom.
-struct HullStage { float4* buf; int cap; unsigned bar; unsigned phase; int resA, nA; };
+struct HullStage { float4* buf; int cap, soff; unsigned bar; unsigned phase; int resA, nA; };
 
 __device__ __forceinline__ void stage_pair(HullStage& hs, Cvx& A, Cvx& B, int lane) {
   bool needA = A.type == GEOM_MESH && A.nvert <= hs.cap && A.mesh != hs.resA;
@@ -1025,8 +1079,8 @@ __device__ __forceinline__ void stage_pair(HullStage& hs, Cvx& A, Cvx& B, int la
         : "memory");
     hs.phase ^= 1u;
   }
-  if (stA) A.verts = hs.buf;
-  if (stB) B.verts = hs.buf + offB;
+  if (stA) { A.verts = hs.buf; A.soff = hs.soff; }
+  if (stB) { B.verts = hs.buf + offB; B.soff = hs.soff + offB; }
 }
 
 __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& nnarrow, int& flags, HullStage& hs, int lane) {
@@ -1467,8 +1521,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     if (nv <= 32) {
       // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
       // every warp whether any warp of the CTA is still iterating
-      if (!build_hessian32(R, S + o.H, M, S + o.tmpJ, o.ldm, lane, !done, sync)) break;
-      if (!done) chol_solve32(S + o.H, search, nv, o.ldm, lane);
+      if (!hessian_solve32(R, S + o.H, M, S + o.tmpJ, o.ldm, search, lane, !done, !done, sync)) break;
     } else {
       if (sync && !group_sync_or(sync, !done)) break;
       if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
@@ -1538,10 +1591,9 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane,
   float h = m.timestep;
   float *A = S + o.H, *rhs = S + o.v_tmp, *qpos = S + o.qpos, *qvel = S + o.qvel;
   const float *M = S + o.M, *actforce = S + o.actforce;
+  if (active) copy_matrix(A, M, nv, ld, lane);
   if (active) _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
     float* Ai = A + i * ld;
-    const float* Mi = M + i * ld;
-    for (int k = 0; k <= i; k++) Ai[k] = Mi[k];
     Ai[i] += h * PKF(dof_damping)[i];
     for (int a = 0; a < m.nu; a++) {
       float b2 = PKF(actuator_biasprm)[3 * a + 2];
@@ -1558,7 +1610,7 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane,
     rhs[i] = S[o.qfrc_smooth + i] + S[o.qfrc_con + i];
   }
   __syncwarp();
-  if (nv <= 32) { chol_factor32(A, nv, ld, lane, active, sync); if (active) chol_solve32(A, rhs, nv, ld, lane); }
+  if (nv <= 32) chol_solve32(A, nv, ld, rhs, lane, active, sync);
   else if (active) { chol_factor(A, nv, ld, lane); chol_solve(A, rhs, nv, ld, lane); }
   if (!active) return;
   _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
@@ -1698,7 +1750,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
   int bar = (1 + grp) | ((nwg * 32) << 8);
   __shared__ __align__(8) unsigned long long hull_bar[8];
   HullStage hs;
-  hs.buf = reinterpret_cast<float4*>(S + o.J); hs.cap = (m.maxcrow * o.ldj) / 4; hs.phase = 0; hs.resA = -1; hs.nA = 0;
+  hs.buf = reinterpret_cast<float4*>(S + o.J); hs.cap = (m.maxcrow * o.ldj) / 4; hs.soff = (int)((S + o.J) - smem) / 4; hs.phase = 0; hs.resA = -1; hs.nA = 0;
   hs.bar = (unsigned)__cvta_generic_to_shared(&hull_bar[warp]);
   if (lane == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs.bar));
@@ -1749,8 +1801,8 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
         {
         int ssync = (attempt == 0 && (a.sync_level & 8)) ? bar : 0;
-        if (active) copy_lower(S + o.H, S + o.M, m.nv, o.ldm, lane);
-        if (m.nv <= 32) { chol_factor32(S + o.H, m.nv, o.ldm, lane, active, ssync); if (active) chol_solve32(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+        if (active) copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
+        if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, active, ssync);
         else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
         cost += 8 * fi.iter + fi.nnarrow;
