@@ -267,7 +267,7 @@ struct Rows {
 // WRITE=true : alpha ignored; writes force/state, returns cost in c_out.
 // WRITE=false: line-search probe; returns cost, derivative g, curvature h (constraint part only).
 template <bool WRITE>
-__device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& c_out, float& g_out, float& h_out, int lane) {
+__device__ __noinline__ float4 eval_constraints(const Rows R, float alpha, int lane) {
   const float *jar = R.jar, *jv = R.jv, *eD = R.eD, *eR = R.eR, *efl = R.efl;
   float c = 0, g = 0, h = 0;
   _Pragma("unroll 1") for (int r = lane; r < R.nefc; r += 32) {
@@ -332,9 +332,10 @@ __device__ __noinline__ void eval_constraints(const Rows R, float alpha, float& 
     }
     if (WRITE) for (int j = 0; j < dim; j++) R.info[i + j] = (R.info[i + j] & ~0xF0) | (st << 4);
   }
-  c_out = warp_sum(c);
-  if (!WRITE) { g_out = warp_sum(g); h_out = warp_sum(h); }
+  float4 res = make_float4(warp_sum(c), 0.f, 0.f, 0.f);
+  if (!WRITE) { res.y = warp_sum(g); res.z = warp_sum(h); }
   if (WRITE) __syncwarp();
+  return res;   // cost, derivative, curvature
 }
 
 // y[r] = J[r,:] . x for all rows (simple rows + dense contact rows)
@@ -493,8 +494,10 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
       int dim = __float_as_int(con[C_DIM]);
       float mu = con[C_MU], U[6], sc[6], T2 = 0;
       sc[0] = mu; U[0] = R.jar[r] * mu;
-#pragma unroll 1
-      for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = R.jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
+#pragma unroll
+      for (int j = 1; j < 6; j++) {   // fixed bound: U / sc stay in registers
+        sc[j] = j < dim ? con[C_FRICTION + j - 1] : 0.f; U[j] = j < dim ? R.jar[r + j] * sc[j] : 0.f; T2 += U[j] * U[j];
+      }
       float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
       float iT = 1.0f / T;
       const float* Jc = R.J + (r - ns) * ldj;
@@ -505,10 +508,12 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
       float c = -Dm * mu * (N - mu * T) * iT;
       int jl = min(lane, ldj - 1);
       float vg = mu * Jc[jl], vu = 0;
-#pragma unroll 1
-      for (int j = 1; j < dim; j++) {
-        float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + jl];
-        vu = fmaf(w, Jj, vu); vg = fmaf(-mu * w, Jj, vg);
+#pragma unroll
+      for (int j = 1; j < 6; j++) {
+        if (j < dim) {
+          float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + jl];
+          vu = fmaf(w, Jj, vu); vg = fmaf(-mu * w, Jj, vg);
+        }
       }
       __syncwarp();
       if (lane < ldj) { tmpJ[lane] = lane < nv ? vg : 0.f; tmpJ[ldj + lane] = lane < nv ? vu : 0.f; }
@@ -516,7 +521,7 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
       rank1_row<NT>(h, (lane < nv) ? Dm * vg : 0.f, tmpJ);
       rank1_row<NT>(h, (lane < nv) ? -c * vu : 0.f, tmpJ + ldj);
 #pragma unroll 1
-      for (int j = 1; j < dim; j++) rank1_row<NT>(h, (lane < nv) ? c * sc[j] * sc[j] * Jc[j * ldj + jl] : 0.f, Jc + j * ldj);
+      for (int j = 1; j < dim; j++) { float fj = con[C_FRICTION + j - 1]; rank1_row<NT>(h, (lane < nv) ? c * fj * fj * Jc[j * ldj + jl] : 0.f, Jc + j * ldj); }
       r += dim - 1;
     }
   }
@@ -942,20 +947,22 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
   }
 }
 
-struct ContactOut { float dist[4], pos[4][3], n[3]; int count; };
 
 // analytic plane-vs-primitive routines and MPR for the rest; fills up to 4 contacts
-__device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, float margin, ContactOut& out, int lane) {
-  out.count = 0;
+__device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, float margin, int so, int lane) {
+  // result record in shared memory (every lane writes the same values): count, normal[3], dist[4], pos[4][3]
+  int& OC = reinterpret_cast<int&>(smem[so]);
+  float *ON = smem + so + 1, *OD = smem + so + 4, *OP = smem + so + 8;
+  OC = 0;
   if (A.type == GEOM_PLANE) {
     float n[3] = {A.mat[2], A.mat[5], A.mat[8]};
-    out.n[0] = n[0]; out.n[1] = n[1]; out.n[2] = n[2];
+    ON[0] = n[0]; ON[1] = n[1]; ON[2] = n[2];
     float dif[3] = {B.pos[0] - A.pos[0], B.pos[1] - A.pos[1], B.pos[2] - A.pos[2]};
     if (B.type == GEOM_SPHERE) {
       float r = B.size[0], dist = dot3(dif, n) - r;
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) out.pos[0][k] = B.pos[k] - n[k] * (r + 0.5f * dist);
-      out.dist[0] = dist; out.count = 1;
+      for (int k = 0; k < 3; k++) OP[3 * 0 + k] = B.pos[k] - n[k] * (r + 0.5f * dist);
+      OD[0] = dist; OC = 1;
     } else if (B.type == GEOM_CYLINDER) {
       float axis[3] = {B.mat[2], B.mat[5], B.mat[8]}, vec[3];
       float r = B.size[0], h = B.size[1];
@@ -971,12 +978,12 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
       float dist = dist0 + prjaxis + prjvec;
       if (dist > margin) return;
       int c = 0;
-      for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
-      out.dist[c++] = dist;
+      for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
+      OD[c++] = dist;
       dist = dist0 - prjaxis + prjvec;
       if (dist <= margin) {
-        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
-        out.dist[c++] = dist;
+        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
+        OD[c++] = dist;
       }
       float prjvec1 = -prjvec * 0.5f;
       dist = dist0 + prjaxis + prjvec1;
@@ -985,14 +992,14 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         cross3(vec1, vec, axis); normalize3(vec1);
         float s = r * 0.8660254037844386f;
         vec1[0] *= s; vec1[1] *= s; vec1[2] *= s;
-        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-        out.dist[c++] = dist;
+        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+        OD[c++] = dist;
         if (c < 4) {
-          for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-          out.dist[c++] = dist;
+          for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+          OD[c++] = dist;
         }
       }
-      out.count = c;
+      OC = c;
     } else if (B.type == GEOM_BOX) {
       float dist = dot3(dif, n);
       int c = 0;
@@ -1003,36 +1010,35 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         float ldist = dot3(n, vec);
         if (dist + ldist > margin || ldist > 0) continue;
         float cd = dist + ldist;
-        for (int k = 0; k < 3; k++) out.pos[c][k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
-        out.dist[c++] = cd;
+        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
+        OD[c++] = cd;
       }
-      out.count = c;
+      OC = c;
     } else if (B.type == GEOM_MESH) {
       float nd[3] = {-n[0], -n[1], -n[2]}, s[3];
       support(B, nd, s, lane);
       float d3[3] = {s[0] - A.pos[0], s[1] - A.pos[1], s[2] - A.pos[2]};
       float dist = dot3(d3, n);
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) out.pos[0][k] = s[k] - n[k] * 0.5f * dist;
-      out.dist[0] = dist; out.count = 1;
+      for (int k = 0; k < 3; k++) OP[3 * 0 + k] = s[k] - n[k] * 0.5f * dist;
+      OD[0] = dist; OC = 1;
     }
   } else {
     float depth, dir[3], pos[3];
     if (!mpr_penetration(A, B, &depth, dir, pos, lane)) return;
     if (dot3(dir, dir) < 0.5f) return;
-    out.n[0] = dir[0]; out.n[1] = dir[1]; out.n[2] = dir[2];
-    out.pos[0][0] = pos[0]; out.pos[0][1] = pos[1]; out.pos[0][2] = pos[2];
-    out.dist[0] = -depth; out.count = 1;
+    ON[0] = dir[0]; ON[1] = dir[1]; ON[2] = dir[2];
+    OP[3 * 0 + 0] = pos[0]; OP[3 * 0 + 1] = pos[1]; OP[3 * 0 + 2] = pos[2];
+    OD[0] = -depth; OC = 1;
   }
 }
 
 // Single noinline body of the narrowphase; the operands are copied into registers once (they arrive through
 // local memory) and everything below (MPR, support scans) is inlined so that they stay there.
-__device__ __noinline__ void narrow_pair(const Cvx& A_, const Cvx& B_, float margin, ContactOut& out_, int lane) {
+__device__ __noinline__ void narrow_pair(const Cvx& A_, const Cvx& B_, float margin, int so, int lane) {
   const Cvx A = A_, B = B_;
-  ContactOut out;
-  narrow_pair_body(A, B, margin, out, lane);
-  out_ = out;
+  narrow_pair_body(A, B, margin, so, lane);
+  __syncwarp();
 }
 
 // Hull staging: MPR calls the support function of both hulls 20-60 times per query, each call a
@@ -1158,29 +1164,32 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       int pair = base + bit;
       int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
       Cvx A, B;
-      ContactOut out;
+      const int so = (int)(S + o.e_R - smem);   // narrowphase result record: the row arrays are not built yet
       make_cvx(m, S, c1, A);
       make_cvx(m, S, c2, B);
       if (A.type != GEOM_PLANE) stage_pair(hs, A, B, lane);
-      narrow_pair(A, B, m.pair_margin[pair], out, lane);
-      for (int c = 0; c < out.count; c++) {
+      narrow_pair(A, B, m.pair_margin[pair], so, lane);
+      const int ocount = __float_as_int(smem[so]);
+      const float *on = smem + so + 1, *od = smem + so + 4, *op = smem + so + 8;
+      for (int c = 0; c < ocount; c++) {
         if (ncon >= m.maxcon) { flags |= 2; break; }
         if (lane == 0) {
           float* cr = S + o.con + ncon * CON_STRIDE;
-          float x[3] = {out.n[0], out.n[1], out.n[2]}, y[3] = {0, 1, 0}, z[3];
+          float x[3] = {on[0], on[1], on[2]}, y[3] = {0, 1, 0}, z[3];
           if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
           float d = dot3(x, y);
           y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
           normalize3(y);
           cross3(z, x, y);
-          for (int k = 0; k < 3; k++) { cr[C_POS + k] = out.pos[c][k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
-          cr[C_DIST] = out.dist[c]; cr[C_MU] = 0;
+          for (int k = 0; k < 3; k++) { cr[C_POS + k] = op[3 * c + k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
+          cr[C_DIST] = od[c]; cr[C_MU] = 0;
           cr[C_DIM] = __int_as_float(m.pair_condim[pair]); cr[C_PAIR] = __int_as_float(pair); cr[C_EFC] = __int_as_float(-1);
           cr[C_BODY1] = __int_as_float(PKI(cg_bodyid)[c1]); cr[C_BODY2] = __int_as_float(PKI(cg_bodyid)[c2]);
           for (int k = 0; k < 5; k++) cr[C_FRICTION + k] = m.pair_friction[5 * pair + k];
         }
         ncon++;
       }
+      __syncwarp();
     }
   }
   __syncwarp();
@@ -1432,8 +1441,8 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
       for (int i = 0; i < nv; i++) vel += Jr[i] * qvel[i];
       float diag = (r < 3) ? (PKF(body_invweight0)[2 * b1] + PKF(body_invweight0)[2 * b2])
                            : (PKF(body_invweight0)[2 * b1 + 1] + PKF(body_invweight0)[2 * b2 + 1]);
-      float R, aref, solref[2] = {m.pair_solref[2 * pair], m.pair_solref[2 * pair + 1]}, solimp[5];
-      for (int k = 0; k < 5; k++) solimp[k] = m.pair_solimp[5 * pair + k];
+      float R, aref;
+      const float *solref = m.pair_solref + 2 * pair, *solimp = m.pair_solimp + 5 * pair;
       float inclmargin = m.pair_margin[pair] - m.pair_gap[pair];
       row_params(m.timestep, solref, solimp, r == 0 ? con[C_DIST] : 0.f, r == 0 ? inclmargin : 0.f, diag, vel, &R, &aref);
       eR[row] = R; earef[row] = aref; efl[row] = 0;
@@ -1477,7 +1486,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   R.sc1 = S + o.s_c1; R.sc2 = S + o.s_c2; R.J = S + o.J; R.eD = S + o.e_D; R.eR = S + o.e_R; R.efl = S + o.e_floss;
   R.con = S + o.con; R.jar = jar; R.jv = jv; R.force = force; R.ns = ns; R.nefc = nefc; R.ncon = ncon; R.ldj = o.ldj; R.nv = nv;
   float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
-  float cw, cs, dg, dh;
+  float cw, cs;
   float cost = 0;
   if (!done) {
   // warm start vs. unconstrained acceleration: keep the cheaper one
@@ -1487,7 +1496,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   symv(Ma, M, qacc, nv, o.ldm, lane);
   _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] -= aref[r];
   __syncwarp();
-  eval_constraints<true>(R, 0.f, cw, dg, dh, lane);
+  cw = eval_constraints<true>(R, 0.f, lane).x;
   {
     float gsum = 0;
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
@@ -1496,14 +1505,14 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   mul_J(R, jv, qas, lane);
   _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) { float t = jv[r] - aref[r]; jv[r] = t - jar[r]; }
   __syncwarp();
-  eval_constraints<false>(R, 1.0f, cs, dg, dh, lane);
+  cs = eval_constraints<false>(R, 1.0f, lane).x;
   cost = cw;
   if (!(cw <= cs)) {  // also catches NaN warm starts
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += jv[r];
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qacc[i] = qas[i];
     __syncwarp();
     symv(Ma, M, qacc, nv, o.ldm, lane);
-    eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
+    cost = eval_constraints<true>(R, 0.f, lane).x;
   }
   }
   int iter = 0;
@@ -1539,16 +1548,14 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     q1 = warp_sum(q1); q2 = warp_sum(q2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
-    float p0, p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
-    eval_constraints<false>(R, 0.f, p0, p1, p2, lane);
-    p1 += q1; p2 += q2;
+    float p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
+    { float4 e = eval_constraints<false>(R, 0.f, lane); p1 = e.y + q1; p2 = e.z + q2; }
     if (!(p1 < 0) || !(p2 > 0)) { done = true; continue; }
     float d0 = p1;
     dlo = p1;
     a = -p1 / p2;
     for (int it = 0; it < m.ls_iterations; it++) {
-      eval_constraints<false>(R, a, p0, p1, p2, lane);
-      p1 += q1 + a * q2; p2 += q2;
+      { float4 e = eval_constraints<false>(R, a, lane); p1 = e.y + q1 + a * q2; p2 = e.z + q2; }
       if (fabsf(p1) < gtol || fabsf(p1) < 1e-6f * fabsf(d0)) break;
       if (p1 < 0) { lo = a; dlo = p1; } else { hi = a; dhi = p1; }
       float an = (p2 > 0) ? a - p1 / p2 : -1.f;
@@ -1568,7 +1575,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
     __syncwarp();
     float oldcost = cost;
-    eval_constraints<true>(R, 0.f, cost, dg, dh, lane);
+    cost = eval_constraints<true>(R, 0.f, lane).x;
     {
       float gsum = 0;
       _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) gsum += 0.5f * (Ma[i] - qs[i]) * (qacc[i] - qas[i]);
