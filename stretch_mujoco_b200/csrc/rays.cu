@@ -25,50 +25,82 @@
 
 // ----------------------------------------------------------------------------- host: BVH build
 namespace {
+// BVH2 with the CHILDREN's boxes stored in the parent (one 64-byte node per visit, no re-test at pop):
+//   n0 = (L.lo.xyz, L.hi.x)  n1 = (L.hi.yz, R.lo.xy)  n2 = (R.lo.z, R.hi.xyz)  n3 = (refL, refR, cntL, cntR) as ints
+// ref >= 0: internal node index; ref < 0: leaf, first triangle = ~ref (global, leaf order), cnt triangles.
 struct HostBVH {
-  std::vector<float4> nodes;  // 2 per node
+  std::vector<float4> nodes;  // 4 per internal node
   std::vector<float4> tris;   // 3 per triangle (v0, e1, e2), leaf order
 };
+struct Box { float lo[3], hi[3]; };
+static inline void box_init(Box& b) { for (int k = 0; k < 3; k++) { b.lo[k] = 1e30f; b.hi[k] = -1e30f; } }
+static inline void box_add(Box& b, const Box& o) { for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], o.lo[k]); b.hi[k] = std::max(b.hi[k], o.hi[k]); } }
+static inline float box_area(const Box& b) {
+  float d[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
+  if (d[0] < 0) return 0.f;
+  return 2.f * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]);
+}
+static float as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 
 struct Builder {
-  const float* V; const int* F; std::vector<int> order; std::vector<float> cen; HostBVH* out; int tri_base;
-  void bounds(int t, float* lo, float* hi) const {
-    const int* f = F + 3 * t;
-    for (int k = 0; k < 3; k++) {
-      float a = V[3 * f[0] + k], b = V[3 * f[1] + k], c = V[3 * f[2] + k];
-      lo[k] = std::min(a, std::min(b, c)); hi[k] = std::max(a, std::max(b, c));
-    }
-  }
-  int build(int first, int count) {
-    int id = (int)out->nodes.size() / 2;
-    out->nodes.push_back(make_float4(0, 0, 0, 0)); out->nodes.push_back(make_float4(0, 0, 0, 0));
-    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+  const float* V; const int* F; std::vector<int> order; std::vector<float> cen; std::vector<Box> tb; HostBVH* out; int tri_base;
+  // returns the child reference and its bounds / triangle count
+  int build(int first, int count, Box& bounds, int& cnt) {
+    Box cb; box_init(bounds); box_init(cb);
     for (int i = first; i < first + count; i++) {
-      float a[3], b[3];
-      bounds(order[i], a, b);
-      for (int k = 0; k < 3; k++) {
-        lo[k] = std::min(lo[k], a[k]); hi[k] = std::max(hi[k], b[k]);
-        clo[k] = std::min(clo[k], cen[3 * order[i] + k]); chi[k] = std::max(chi[k], cen[3 * order[i] + k]);
-      }
+      box_add(bounds, tb[order[i]]);
+      for (int k = 0; k < 3; k++) { cb.lo[k] = std::min(cb.lo[k], cen[3 * order[i] + k]); cb.hi[k] = std::max(cb.hi[k], cen[3 * order[i] + k]); }
     }
     int ax = 0;
-    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
-    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
-    int left, right;
-    if (count <= 4 || !(chi[ax] > clo[ax])) {
-      left = ~(tri_base + first); right = count;  // leaf: first triangle (global index, complemented), count
-    } else {
-      int mid = first + count / 2;
+    if (cb.hi[1] - cb.lo[1] > cb.hi[ax] - cb.lo[ax]) ax = 1;
+    if (cb.hi[2] - cb.lo[2] > cb.hi[ax] - cb.lo[ax]) ax = 2;
+    if (count <= 4 || !(cb.hi[ax] > cb.lo[ax])) { cnt = count; return ~(tri_base + first); }
+    // binned surface-area heuristic over the three axes (16 bins); median split as the fallback
+    const int NB = 16;
+    float best_cost = 1e30f; int best_ax = -1, best_bin = -1;
+    for (int a = 0; a < 3; a++) {
+      float ext = cb.hi[a] - cb.lo[a];
+      if (!(ext > 0)) continue;
+      Box bb[NB]; int bc[NB];
+      for (int b = 0; b < NB; b++) { box_init(bb[b]); bc[b] = 0; }
+      for (int i = first; i < first + count; i++) {
+        int b = std::min(NB - 1, (int)(NB * (cen[3 * order[i] + a] - cb.lo[a]) / ext));
+        box_add(bb[b], tb[order[i]]); bc[b]++;
+      }
+      float la[NB]; int lc[NB]; Box acc; box_init(acc); int n = 0;
+      for (int b = 0; b < NB - 1; b++) { box_add(acc, bb[b]); n += bc[b]; la[b] = box_area(acc); lc[b] = n; }
+      box_init(acc); n = 0;
+      for (int b = NB - 1; b > 0; b--) {
+        box_add(acc, bb[b]); n += bc[b];
+        if (lc[b - 1] == 0 || n == 0) continue;
+        float cost = la[b - 1] * lc[b - 1] + box_area(acc) * n;
+        if (cost < best_cost) { best_cost = cost; best_ax = a; best_bin = b; }
+      }
+    }
+    int mid;
+    if (best_ax >= 0) {
+      float ext = cb.hi[best_ax] - cb.lo[best_ax];
+      auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int t) {
+        return std::min(NB - 1, (int)(NB * (cen[3 * t + best_ax] - cb.lo[best_ax]) / ext)) < best_bin; });
+      mid = (int)(it - order.begin());
+    } else mid = first;
+    if (mid <= first || mid >= first + count) {
+      mid = first + count / 2;
       std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
                        [&](int a, int b) { return cen[3 * a + ax] < cen[3 * b + ax]; });
-      left = build(first, mid - first);
-      right = build(mid, first + count - mid);
     }
-    out->nodes[2 * id] = make_float4(lo[0], lo[1], lo[2], __int_as_float_host(left));
-    out->nodes[2 * id + 1] = make_float4(hi[0], hi[1], hi[2], __int_as_float_host(right));
+    int id = (int)out->nodes.size() / 4;
+    for (int k = 0; k < 4; k++) out->nodes.push_back(make_float4(0, 0, 0, 0));
+    Box lb, rb; int lc2, rc2;
+    int lref = build(first, mid - first, lb, lc2);
+    int rref = build(mid, first + count - mid, rb, rc2);
+    out->nodes[4 * id] = make_float4(lb.lo[0], lb.lo[1], lb.lo[2], lb.hi[0]);
+    out->nodes[4 * id + 1] = make_float4(lb.hi[1], lb.hi[2], rb.lo[0], rb.lo[1]);
+    out->nodes[4 * id + 2] = make_float4(rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]);
+    out->nodes[4 * id + 3] = make_float4(as_float(lref), as_float(rref), as_float(lc2), as_float(rc2));
+    cnt = count;
     return id;
   }
-  static float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
 };
 }  // namespace
 
@@ -117,17 +149,28 @@ int ss_rays_model_init(ss_model* M) {
   const float* V = ss_blob_f32(&b, "rmesh_vert");
   const int32_t* F = ss_blob_i32(&b, "rmesh_face");
   HostBVH H;
-  std::vector<int> bvhadr(vadr.size(), -1);
+  std::vector<int> bvhadr(vadr.size(), 0), bvhcnt(vadr.size(), 0);
+  std::vector<float4> mbox(2 * vadr.size(), make_float4(0, 0, 0, 0));
   for (size_t mid = 0; mid < vadr.size(); mid++) {
     if (fadr[mid] < 0 || fnum[mid] <= 0) continue;
     Builder B;
     B.V = V + 3 * (size_t)vadr[mid]; B.F = F + 3 * (size_t)fadr[mid]; B.out = &H; B.tri_base = (int)H.tris.size() / 3;
     int nf = fnum[mid];
     B.order.resize(nf); std::iota(B.order.begin(), B.order.end(), 0);
-    B.cen.resize(3 * (size_t)nf);
-    for (int t = 0; t < nf; t++)
-      for (int k = 0; k < 3; k++) B.cen[3 * t + k] = (B.V[3 * B.F[3 * t] + k] + B.V[3 * B.F[3 * t + 1] + k] + B.V[3 * B.F[3 * t + 2] + k]) / 3.0f;
-    bvhadr[mid] = B.build(0, nf);
+    B.cen.resize(3 * (size_t)nf); B.tb.resize(nf);
+    for (int t = 0; t < nf; t++) {
+      const int* f = B.F + 3 * t;
+      for (int k = 0; k < 3; k++) {
+        float a = B.V[3 * f[0] + k], b2 = B.V[3 * f[1] + k], c = B.V[3 * f[2] + k];
+        B.cen[3 * t + k] = (a + b2 + c) / 3.0f;
+        B.tb[t].lo[k] = std::min(a, std::min(b2, c)); B.tb[t].hi[k] = std::max(a, std::max(b2, c));
+      }
+    }
+    Box bounds; int cnt = 0;
+    bvhadr[mid] = B.build(0, nf, bounds, cnt);
+    bvhcnt[mid] = cnt;
+    mbox[2 * mid] = make_float4(bounds.lo[0], bounds.lo[1], bounds.lo[2], 0);
+    mbox[2 * mid + 1] = make_float4(bounds.hi[0], bounds.hi[1], bounds.hi[2], 0);
     for (int i = 0; i < nf; i++) {
       const int* f = B.F + 3 * B.order[i];
       const float *a = B.V + 3 * f[0], *c1 = B.V + 3 * f[1], *c2 = B.V + 3 * f[2];
@@ -136,6 +179,26 @@ int ss_rays_model_init(ss_model* M) {
       H.tris.push_back(make_float4(c2[0] - a[0], c2[1] - a[1], c2[2] - a[2], 0));
     }
   }
+  // per ray-geom record used by the tracing blocks: (type, mesh root ref, root triangle count, body | group << 16),
+  // (rbound, size.xyz), local bounds lo / hi (for the mesh root test and the tile culling)
+  std::vector<float4> rec(4 * rg.size());
+  for (size_t k = 0; k < rg.size(); k++) {
+    int type = t_type[k], mesh = t_mesh[k], ref = 0, cnt = 0;
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) { lo[a] = -t_size[3 * k + a]; hi[a] = t_size[3 * k + a]; }
+    if (type == GEOM_SPHERE) for (int a = 0; a < 3; a++) { lo[a] = -t_size[3 * k]; hi[a] = t_size[3 * k]; }
+    if (type == GEOM_CYLINDER) { lo[0] = lo[1] = -t_size[3 * k]; hi[0] = hi[1] = t_size[3 * k]; lo[2] = -t_size[3 * k + 1]; hi[2] = t_size[3 * k + 1]; }
+    if (type == GEOM_MESH) {
+      bool ok = mesh >= 0 && fnum[mesh] > 0;
+      ref = ok ? bvhadr[mesh] : 0; cnt = ok ? bvhcnt[mesh] : -1;   // cnt < 0: nothing to hit
+      for (int a = 0; a < 3; a++) { lo[a] = ok ? (&mbox[2 * mesh].x)[a] : 0.f; hi[a] = ok ? (&mbox[2 * mesh + 1].x)[a] : 0.f; }
+    }
+    rec[4 * k] = make_float4(as_float(type), as_float(ref), as_float(cnt), as_float(t_body[k] | (t_group[k] << 16)));
+    rec[4 * k + 1] = make_float4(t_rb[k], t_size[3 * k], t_size[3 * k + 1], t_size[3 * k + 2]);
+    rec[4 * k + 2] = make_float4(lo[0], lo[1], lo[2], 0);
+    rec[4 * k + 3] = make_float4(hi[0], hi[1], hi[2], 0);
+  }
+  r.rg_rec = upload(M, rec);
   r.present = 1;
   r.nraygeom = (int)rg.size(); r.nmesh = (int)vadr.size(); r.ngeom = M->dims.ngeom; r.nbody = M->dims.nbody;
   r.ncam = M->dims.ncam; r.nsite = M->dims.nsite;
@@ -216,36 +279,32 @@ __global__ void ray_prepare_kernel(RayModel r, int nenv, const float* __restrict
 
 struct Hit { float t; int k; float n[3]; };  // k = index into the ray-geom list; n = local-frame normal (unnormalised)
 
-__device__ __forceinline__ bool box_hit(const float4 lo, const float4 hi, const float* o, const float* inv, float tmax, float* tnear) {
-  float t0 = 0.f, t1 = tmax;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    float l = (k == 0 ? lo.x : k == 1 ? lo.y : lo.z), h = (k == 0 ? hi.x : k == 1 ? hi.y : hi.z);
-    float a = (l - o[k]) * inv[k], b = (h - o[k]) * inv[k];
-    float mn = fminf(a, b), mx = fmaxf(a, b);
-    t0 = fmaxf(t0, mn); t1 = fminf(t1, mx);
-  }
+// slab test of the ray (o, 1/d) against the box [lo, hi] on [0, tmax]; entry distance in *tnear
+__device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, float hy, float hz, const float* o, const float* inv,
+                                     float tmax, float* tnear) {
+  float ax = (lx - o[0]) * inv[0], bx = (hx - o[0]) * inv[0];
+  float ay = (ly - o[1]) * inv[1], by = (hy - o[1]) * inv[1];
+  float az = (lz - o[2]) * inv[2], bz = (hz - o[2]) * inv[2];
+  float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+  float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
   *tnear = t0;
   return t0 <= t1;
 }
 
-__device__ float trace_mesh(const RayModel& r, int root, const float* o, const float* d, float tmin, float tbest, float* nrm) {
-  float inv[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) inv[k] = 1.0f / (fabsf(d[k]) > 1e-20f ? d[k] : (d[k] < 0 ? -1e-20f : 1e-20f));
+// Nearest triangle hit below the node `ref` (>= 0 internal, < 0 leaf ~first with cnt triangles); the caller has
+// already tested the mesh bounds.  One 64-byte node per visit (children boxes in the parent), nearer child
+// first, the farther one is stacked with its entry distance and dropped at pop time once a closer hit exists.
+__device__ float trace_mesh(const RayModel& r, int ref, int cnt, const float* o, const float* d, const float* inv, float tmin,
+                            float tbest, float* nrm) {
   float best = tbest;  // only hits closer than tbest matter (<0: none yet)
   bool found = false;
-  int stack[40], sp = 0;
-  stack[sp++] = root;
-  while (sp) {
-    int id = stack[--sp];
-    float4 n0 = __ldg(r.bvh + 2 * id), n1 = __ldg(r.bvh + 2 * id + 1);
-    float tn;
-    if (!box_hit(n0, n1, o, inv, best >= 0 ? best : 1e30f, &tn)) continue;
-    int left = __float_as_int(n0.w), right = __float_as_int(n1.w);
-    if (left < 0) {
-      int first = ~left;
-      for (int i = first; i < first + right; i++) {
+  int stack[32], cstk[32], sp = 0;
+  float tstk[32];
+  int cur = ref, ccnt = cnt;
+  while (true) {
+    if (cur < 0) {
+      int first = ~cur;
+      for (int i = first; i < first + ccnt; i++) {
         float4 v0 = __ldg(r.tri + 3 * i), e1 = __ldg(r.tri + 3 * i + 1), e2 = __ldg(r.tri + 3 * i + 2);
         float p[3] = {d[1] * e2.z - d[2] * e2.y, d[2] * e2.x - d[0] * e2.z, d[0] * e2.y - d[1] * e2.x};
         float det = e1.x * p[0] + e1.y * p[1] + e1.z * p[2];
@@ -262,25 +321,55 @@ __device__ float trace_mesh(const RayModel& r, int root, const float* o, const f
           nrm[0] = e1.y * e2.z - e1.z * e2.y; nrm[1] = e1.z * e2.x - e1.x * e2.z; nrm[2] = e1.x * e2.y - e1.y * e2.x;
         }
       }
-    } else if (sp < 38) {
-      // visit the nearer child first
-      float4 l0 = __ldg(r.bvh + 2 * left), l1 = __ldg(r.bvh + 2 * left + 1), r0 = __ldg(r.bvh + 2 * right), r1 = __ldg(r.bvh + 2 * right + 1);
-      float tl, tr;
-      float lim = best >= 0 ? best : 1e30f;
-      bool hl = box_hit(l0, l1, o, inv, lim, &tl), hr = box_hit(r0, r1, o, inv, lim, &tr);
+    } else {
+      const float4* nd = r.bvh + 4 * (size_t)cur;
+      float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+      float lim = best >= 0 ? best : 1e30f, tl, tr;
+      bool hl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, lim, &tl);
+      bool hr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, lim, &tr);
+      int rl = __float_as_int(n3.x), rr = __float_as_int(n3.y), cl = __float_as_int(n3.z), cr = __float_as_int(n3.w);
       if (hl && hr) {
-        if (tl <= tr) { stack[sp++] = right; stack[sp++] = left; } else { stack[sp++] = left; stack[sp++] = right; }
-      } else if (hl) stack[sp++] = left;
-      else if (hr) stack[sp++] = right;
+        bool lfirst = tl <= tr;
+        if (sp < 32) { stack[sp] = lfirst ? rr : rl; cstk[sp] = lfirst ? cr : cl; tstk[sp] = lfirst ? tr : tl; sp++; }
+        cur = lfirst ? rl : rr; ccnt = lfirst ? cl : cr;
+        continue;
+      }
+      if (hl) { cur = rl; ccnt = cl; continue; }
+      if (hr) { cur = rr; ccnt = cr; continue; }
     }
+    // pop the next stacked subtree that can still beat the best hit
+    bool got = false;
+    while (sp) {
+      --sp;
+      if (best >= 0 && tstk[sp] > best) continue;
+      cur = stack[sp]; ccnt = cstk[sp]; got = true;
+      break;
+    }
+    if (!got) break;
   }
   return found ? best : -1.f;
 }
 
+// per-geom record in shared memory: 4 float4 (see ss_rays_model_init)
+#define REC_TYPE(rec) __float_as_int((rec)[0].x)
+#define REC_REF(rec) __float_as_int((rec)[0].y)
+#define REC_CNT(rec) __float_as_int((rec)[0].z)
+#define REC_BODY(rec) (__float_as_int((rec)[0].w) & 0xffff)
+#define REC_GROUP(rec) (__float_as_int((rec)[0].w) >> 16)
+
 // nearest intersection with one geom in its local frame, x >= tmin and (tbest<0 or x<tbest)
-__device__ float trace_geom(const RayModel& r, int k, const float* o, const float* d, float tmin, float tbest, float* nrm) {
-  int type = r.rg_type[k];
-  float s0 = r.rg_size[3 * k], s1 = r.rg_size[3 * k + 1], s2 = r.rg_size[3 * k + 2];
+__device__ float trace_geom(const RayModel& r, const float4* rec, const float* o, const float* d, float tmin, float tbest, float* nrm) {
+  int type = REC_TYPE(rec);
+  float s0 = rec[1].y, s1 = rec[1].z, s2 = rec[1].w;
+  if (type == GEOM_MESH) {
+    int cnt = REC_CNT(rec);
+    if (cnt < 0) return -1.f;
+    float inv[3], tn;
+#pragma unroll
+    for (int k = 0; k < 3; k++) inv[k] = 1.0f / (fabsf(d[k]) > 1e-20f ? d[k] : (d[k] < 0 ? -1e-20f : 1e-20f));
+    if (!slab(rec[2].x, rec[2].y, rec[2].z, rec[3].x, rec[3].y, rec[3].z, o, inv, tbest >= 0 ? tbest : 1e30f, &tn)) return -1.f;
+    return trace_mesh(r, REC_REF(rec), cnt, o, d, inv, tmin, tbest, nrm);
+  }
   if (type == GEOM_PLANE) {
     if (d[2] > -1e-15f) return -1.f;
     float x = -o[2] / d[2];
@@ -334,28 +423,27 @@ __device__ float trace_geom(const RayModel& r, int k, const float* o, const floa
       }
     return best;
   }
-  if (type == GEOM_MESH) {
-    int root = r.rmesh_bvhadr[r.rg_mesh[k]];
-    if (root < 0) return -1.f;
-    return trace_mesh(r, root, o, d, tmin, tbest, nrm);
-  }
   return -1.f;
 }
 
-// nearest hit over a list of geoms (indices into the ray-geom table); xf = this env's transforms in
-// shared or global memory, addressed by ray-geom index
-__device__ Hit trace_scene(const RayModel& r, const float* xf, const int* list, int nlist, const float* pnt, const float* vec,
-                           float tmin, int groupmask, int bodyexclude) {
+// nearest hit over a list of geoms (indices into the ray-geom table); xf / rec = this env's transforms and the
+// geom records in shared memory, addressed by ray-geom index.  FILTER: apply the group mask / body exclusion.
+template <bool FILTER>
+__device__ Hit trace_scene(const RayModel& r, const float* xf, const float4* recs, const int* list, int nlist, const float* pnt,
+                           const float* vec, float tmin, int groupmask, int bodyexclude) {
   Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
   float vv = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
   for (int i = 0; i < nlist; i++) {
     int k = list ? list[i] : i;
-    if (r.rg_body[k] == bodyexclude) continue;
-    if (groupmask && !((groupmask >> r.rg_group[k]) & 1)) continue;
+    const float4* rec = recs + 4 * k;
+    if (FILTER) {
+      if (REC_BODY(rec) == bodyexclude) continue;
+      if (groupmask && !((groupmask >> REC_GROUP(rec)) & 1)) continue;
+    }
     const float* T = xf + 12 * k;
     float dif[3] = {pnt[0] - T[0], pnt[1] - T[1], pnt[2] - T[2]};
-    if (r.rg_type[k] != GEOM_PLANE) {
-      float rb = r.rg_rbound[k];
+    if (REC_TYPE(rec) != GEOM_PLANE) {
+      float rb = rec[1].x;
       float b = vec[0] * dif[0] + vec[1] * dif[1] + vec[2] * dif[2], c = dif[0] * dif[0] + dif[1] * dif[1] + dif[2] * dif[2] - rb * rb;
       if (c > 0 && (b > 0 || b * b - vv * c < 0)) continue;
       if (h.t >= 0 && c > 0) {  // sphere entirely beyond the current best hit
@@ -367,19 +455,29 @@ __device__ Hit trace_scene(const RayModel& r, const float* xf, const int* list, 
     float o[3] = {R[0] * dif[0] + R[3] * dif[1] + R[6] * dif[2], R[1] * dif[0] + R[4] * dif[1] + R[7] * dif[2], R[2] * dif[0] + R[5] * dif[1] + R[8] * dif[2]};
     float d[3] = {R[0] * vec[0] + R[3] * vec[1] + R[6] * vec[2], R[1] * vec[0] + R[4] * vec[1] + R[7] * vec[2], R[2] * vec[0] + R[5] * vec[1] + R[8] * vec[2]};
     float n[3];
-    float x = trace_geom(r, k, o, d, tmin, h.t, n);
+    float x = trace_geom(r, rec, o, d, tmin, h.t, n);
     if (x >= 0 && (h.t < 0 || x < h.t)) { h.t = x; h.k = k; h.n[0] = n[0]; h.n[1] = n[1]; h.n[2] = n[2]; }
   }
   return h;
 }
 
+// stage this env's geom transforms and the (env-independent) geom records in shared memory
+__device__ __forceinline__ void stage_geoms(const RayModel& r, const float* xf, float4* srec, float* sxf, int tid, int nthr) {
+  for (int i = tid; i < r.nraygeom * 4; i += nthr) srec[i] = __ldg(r.rg_rec + i);
+  const float4* xf4 = reinterpret_cast<const float4*>(xf);
+  float4* sxf4 = reinterpret_cast<float4*>(sxf);
+  for (int i = tid; i < r.nraygeom * 3; i += nthr) sxf4[i] = xf4[i];
+}
+#define RAY_SMEM_BYTES(r) ((size_t)(r).nraygeom * (16 + 12) * sizeof(float))
+
 // ----------------------------------------------------------------------------- lidar
 __global__ void lidar_kernel(RayModel r, int nenv, int nsensordata, const float* __restrict__ xpos, const float* __restrict__ xquat,
                              const float* __restrict__ xf_all, float* __restrict__ out, float* __restrict__ sensordata) {
-  extern __shared__ float sxf[];
+  extern __shared__ float4 sm4[];
+  float4* srec = sm4;
+  float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);
   int e = blockIdx.x;
-  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
-  for (int i = threadIdx.x; i < r.nraygeom * 12; i += blockDim.x) sxf[i] = xf[i];
+  stage_geoms(r, xf_all + (size_t)e * r.nraygeom * 12, srec, sxf, threadIdx.x, blockDim.x);
   __syncthreads();
   for (int s = threadIdx.x; s < r.nrange; s += blockDim.x) {
     int site = r.range_site[s], b = r.site_bodyid[site];
@@ -393,7 +491,7 @@ __global__ void lidar_kernel(RayModel r, int nenv, int nsensordata, const float*
     qmul(q, bqq, sq);
     q2m(R, q);
     float dir[3] = {R[2], R[5], R[8]};
-    Hit h = trace_scene(r, sxf, nullptr, r.nraygeom, p, dir, 0.f, 0, b);
+    Hit h = trace_scene<true>(r, sxf, srec, nullptr, r.nraygeom, p, dir, 0.f, 0, b);
     float dist = h.t;
     float cut = r.range_cutoff[s];
     if (dist >= 0 && cut > 0 && dist > cut) dist = cut;
@@ -405,15 +503,16 @@ __global__ void lidar_kernel(RayModel r, int nenv, int nsensordata, const float*
 __global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restrict__ xf_all, const float* __restrict__ origin,
                             const float* __restrict__ dir, int groupmask, int bodyexclude, float* __restrict__ dist,
                             int32_t* __restrict__ geom) {
-  extern __shared__ float sxf[];
+  extern __shared__ float4 sm4[];
+  float4* srec = sm4;
+  float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);
   int e = blockIdx.x;
-  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
-  for (int i = threadIdx.x; i < r.nraygeom * 12; i += blockDim.x) sxf[i] = xf[i];
+  stage_geoms(r, xf_all + (size_t)e * r.nraygeom * 12, srec, sxf, threadIdx.x, blockDim.x);
   __syncthreads();
   for (int s = threadIdx.x; s < nray; s += blockDim.x) {
     size_t k = (size_t)e * nray + s;
     float p[3] = {origin[3 * k], origin[3 * k + 1], origin[3 * k + 2]}, d[3] = {dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]};
-    Hit h = trace_scene(r, sxf, nullptr, r.nraygeom, p, d, 0.f, groupmask, bodyexclude);
+    Hit h = trace_scene<true>(r, sxf, srec, nullptr, r.nraygeom, p, d, 0.f, groupmask, bodyexclude);
     dist[k] = h.t;
     if (geom) geom[k] = h.k >= 0 ? r.rg_geom[h.k] : -1;
   }
@@ -421,19 +520,21 @@ __global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restr
 
 // ----------------------------------------------------------------------------- camera
 #define TILE 16
+#define MAXLIGHT 8
 __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env_begin, int cam, int W, int H, float fovy_deg,
                                                              const float* __restrict__ xpos, const float* __restrict__ xquat,
                                                              const float* __restrict__ xf_all, uint8_t* __restrict__ rgb,
                                                              float* __restrict__ depth, float depth_limit) {
-  extern __shared__ float sm[];
-  float* sxf = sm;                                  // [nraygeom*12]
-  int* list = (int*)(sm + r.nraygeom * 12);         // [nraygeom]
-  int* flag = list + r.nraygeom;                    // [nraygeom]
+  extern __shared__ float4 sm4[];
+  float4* srec = sm4;                                              // [nraygeom*4]
+  float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);     // [nraygeom*12]
+  int* list = (int*)(sxf + r.nraygeom * 12);                       // [nraygeom]
+  int* flag = list + r.nraygeom;                                   // [nraygeom]
   __shared__ int nlist;
-  __shared__ float cam_eye[3], cam_R[9];
+  __shared__ float cam_eye[3], cam_R[9], focal;
+  __shared__ float lvec[MAXLIGHT][4];   // world direction towards the light (w = 0) or its position (w = 1); slot 0 = headlight
   int le = blockIdx.z, e = env_begin + le, tid = threadIdx.y * TILE + threadIdx.x;
-  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
-  for (int i = tid; i < r.nraygeom * 12; i += TILE * TILE) sxf[i] = xf[i];
+  stage_geoms(r, xf_all + (size_t)e * r.nraygeom * 12, srec, sxf, tid, TILE * TILE);
   if (tid == 0) {
     int b = r.cam_bodyid[cam];
     const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
@@ -446,31 +547,65 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
     cam_eye[2] = bp[2] + Rb[6] * cp[0] + Rb[7] * cp[1] + Rb[8] * cp[2];
     qmul(q, bqq, cq);
     q2m(cam_R, q);
+    focal = 0.5f * H / tanf(fovy_deg * 3.14159265358979f / 360.0f);
+    lvec[0][0] = cam_R[2]; lvec[0][1] = cam_R[5]; lvec[0][2] = cam_R[8]; lvec[0][3] = 0.f;   // headlight: -forward = +z of the camera frame
+  }
+  if (rgb && tid >= 32 && tid < 32 + r.nlight && tid < 32 + MAXLIGHT - 1) {
+    int l = tid - 32, b = r.light_bodyid[l];
+    const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+    float Rb[9], bqq[4] = {bq[0], bq[1], bq[2], bq[3]};
+    q2m(Rb, bqq);
+    float* L = lvec[l + 1];
+    if (r.light_directional[l]) {
+      const float* ld = r.light_dir + 3 * l;
+      L[0] = -(Rb[0] * ld[0] + Rb[1] * ld[1] + Rb[2] * ld[2]); L[1] = -(Rb[3] * ld[0] + Rb[4] * ld[1] + Rb[5] * ld[2]);
+      L[2] = -(Rb[6] * ld[0] + Rb[7] * ld[1] + Rb[8] * ld[2]); L[3] = 0.f;
+    } else {
+      const float* lp = r.light_pos + 3 * l;
+      L[0] = bp[0] + Rb[0] * lp[0] + Rb[1] * lp[1] + Rb[2] * lp[2];
+      L[1] = bp[1] + Rb[3] * lp[0] + Rb[4] * lp[1] + Rb[5] * lp[2];
+      L[2] = bp[2] + Rb[6] * lp[0] + Rb[7] * lp[1] + Rb[8] * lp[2]; L[3] = 1.f;
+    }
   }
   __syncthreads();
-  float f = 0.5f * H / tanf(fovy_deg * 3.14159265358979f / 360.0f);
+  float f = focal;
   float znear = r.znear * r.extent, zfar = r.zfar * r.extent;
-  // tile frustum culling: geoms whose bounding sphere misses the tile's pyramid are dropped
+  // tile frustum culling: geoms whose bounding sphere, then oriented bounding box, misses the tile's pyramid are dropped
   {
     float x0 = (blockIdx.x * TILE - 0.5f * W) / f, x1 = (fminf((blockIdx.x + 1) * TILE, (float)W) - 0.5f * W) / f;
     float y0 = -((blockIdx.y * TILE) - 0.5f * H) / f, y1 = -(fminf((blockIdx.y + 1) * TILE, (float)H) - 0.5f * H) / f;  // y0 > y1
+    float il = rsqrtf(1 + x0 * x0), ir = rsqrtf(1 + x1 * x1), it = rsqrtf(1 + y0 * y0), ib = rsqrtf(1 + y1 * y1);
+    // inward unit normals of the four side planes through the eye (camera frame: looks down -z, +y up)
+    float pn[4][3] = {{il, 0.f, x0 * il}, {-ir, 0.f, -x1 * ir}, {0.f, -it, -y0 * it}, {0.f, ib, y1 * ib}};
     for (int k = tid; k < r.nraygeom; k += TILE * TILE) {
+      const float4* rec = srec + 4 * k;
       bool keep = true;
-      if (!((0x7 >> r.rg_group[k]) & 1)) keep = false;  // camera sees geom groups 0..2 (collision group 3 hidden)
-      else if (r.rg_type[k] != GEOM_PLANE) {
+      if (!((0x7 >> REC_GROUP(rec)) & 1)) keep = false;  // camera sees geom groups 0..2 (collision group 3 hidden)
+      else if (REC_TYPE(rec) != GEOM_PLANE) {
         const float* T = sxf + 12 * k;
+        const float* R = T + 3;
         float dw[3] = {T[0] - cam_eye[0], T[1] - cam_eye[1], T[2] - cam_eye[2]};
-        // camera-frame centre (camera looks down -z, +y up)
         float c[3] = {cam_R[0] * dw[0] + cam_R[3] * dw[1] + cam_R[6] * dw[2], cam_R[1] * dw[0] + cam_R[4] * dw[1] + cam_R[7] * dw[2],
                       cam_R[2] * dw[0] + cam_R[5] * dw[1] + cam_R[8] * dw[2]};
-        float rb = r.rg_rbound[k];
+        float rb = rec[1].x;
         if (-c[2] < znear - rb) keep = false;
-        // side planes through the eye: left (x >= x0*(-z)), right, top, bottom; normals normalised
-        float il = rsqrtf(1 + x0 * x0), ir = rsqrtf(1 + x1 * x1), it = rsqrtf(1 + y0 * y0), ib = rsqrtf(1 + y1 * y1);
-        if ((c[0] + x0 * c[2]) * il < -rb) keep = false;    // left:  x - x0*(-z) >= 0
-        if ((-c[0] - x1 * c[2]) * ir < -rb) keep = false;   // right: x1*(-z) - x >= 0
-        if ((-c[1] - y0 * c[2]) * it < -rb) keep = false;   // top:   y0*(-z) - y >= 0
-        if ((c[1] + y1 * c[2]) * ib < -rb) keep = false;    // bottom
+        for (int p = 0; p < 4 && keep; p++)
+          if (pn[p][0] * c[0] + pn[p][1] * c[1] + pn[p][2] * c[2] < -rb) keep = false;
+        if (keep) {
+          // oriented box: centre and half extents in the geom frame, axes = columns of cam_R^T R
+          float hc[3] = {0.5f * (rec[2].x + rec[3].x), 0.5f * (rec[2].y + rec[3].y), 0.5f * (rec[2].z + rec[3].z)};
+          float hh[3] = {0.5f * (rec[3].x - rec[2].x), 0.5f * (rec[3].y - rec[2].y), 0.5f * (rec[3].z - rec[2].z)};
+          float A[9];   // A = cam_R^T * R (camera-from-geom rotation)
+          for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) A[3 * i + j] = cam_R[i] * R[j] + cam_R[3 + i] * R[3 + j] + cam_R[6 + i] * R[6 + j];
+          float bc[3];
+          for (int i = 0; i < 3; i++) bc[i] = c[i] + A[3 * i] * hc[0] + A[3 * i + 1] * hc[1] + A[3 * i + 2] * hc[2];
+          for (int p = 0; p < 4 && keep; p++) {
+            float dist = pn[p][0] * bc[0] + pn[p][1] * bc[1] + pn[p][2] * bc[2], rad = 0.f;
+            for (int j = 0; j < 3; j++) rad += fabsf(pn[p][0] * A[j] + pn[p][1] * A[3 + j] + pn[p][2] * A[6 + j]) * hh[j];
+            if (dist < -rad * 1.0001f - 1e-6f) keep = false;
+          }
+        }
       }
       flag[k] = keep;
     }
@@ -493,7 +628,7 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
   float dl[3] = {(u + 0.5f - 0.5f * W) / f, -(v + 0.5f - 0.5f * H) / f, -1.0f};
   float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
                  cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
-  Hit h = trace_scene(r, sxf, list, nlist, cam_eye, dw, znear, 0, -1);
+  Hit h = trace_scene<false>(r, sxf, srec, list, nlist, cam_eye, dw, znear, 0, -1);
   float x = h.t;
   if (x < 0 || x > zfar) { x = zfar; h.k = -1; }
   size_t pix = ((size_t)le * H + v) * W + u;
@@ -517,27 +652,17 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
       if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
       for (int a = 0; a < 3; a++) col[a] = sh[a] * sh[6];
       float shininess = fmaxf(sh[5] * 128.0f, 1.0f);
-      for (int l = -1; l < r.nlight; l++) {
+      int nl_ = min(r.nlight, MAXLIGHT - 1);
+      for (int l = -1; l < nl_; l++) {
         float L[3], amb[3], dif[3], spc[3];
+        const float* lv = lvec[l + 1];
         if (l < 0) {
           if (!r.headlight_active) continue;
-          L[0] = cam_R[2]; L[1] = cam_R[5]; L[2] = cam_R[8];   // -forward = +z of the camera frame
+          L[0] = lv[0]; L[1] = lv[1]; L[2] = lv[2];
           for (int a = 0; a < 3; a++) { amb[a] = r.headlight[a]; dif[a] = r.headlight[3 + a]; spc[a] = r.headlight[6 + a]; }
         } else {
-          int b = r.light_bodyid[l];
-          const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
-          float Rb[9], bqq[4] = {bq[0], bq[1], bq[2], bq[3]};
-          q2m(Rb, bqq);
-          if (r.light_directional[l]) {
-            const float* ld = r.light_dir + 3 * l;
-            L[0] = -(Rb[0] * ld[0] + Rb[1] * ld[1] + Rb[2] * ld[2]); L[1] = -(Rb[3] * ld[0] + Rb[4] * ld[1] + Rb[5] * ld[2]);
-            L[2] = -(Rb[6] * ld[0] + Rb[7] * ld[1] + Rb[8] * ld[2]);
-          } else {
-            const float* lp = r.light_pos + 3 * l;
-            L[0] = bp[0] + Rb[0] * lp[0] + Rb[1] * lp[1] + Rb[2] * lp[2] - pos[0];
-            L[1] = bp[1] + Rb[3] * lp[0] + Rb[4] * lp[1] + Rb[5] * lp[2] - pos[1];
-            L[2] = bp[2] + Rb[6] * lp[0] + Rb[7] * lp[1] + Rb[8] * lp[2] - pos[2];
-          }
+          if (lv[3] == 0.f) { L[0] = lv[0]; L[1] = lv[1]; L[2] = lv[2]; }
+          else { L[0] = lv[0] - pos[0]; L[1] = lv[1] - pos[1]; L[2] = lv[2] - pos[2]; }
           float il = rsqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
           L[0] *= il; L[1] *= il; L[2] *= il;
           for (int a = 0; a < 3; a++) { amb[a] = r.light_ambient[3 * l + a]; dif[a] = r.light_diffuse[3 * l + a]; spc[a] = r.light_specular[3 * l + a]; }
@@ -578,7 +703,7 @@ extern "C" int ss_batch_lidar(ss_batch* B, float* out_dev, ss_stream s) {
   if (prepare(B, st) != 0) return -1;
   const RayModel& r = B->model->rm;
   if (r.nrange == 0) return ss_fail("model has no rangefinder sensors");
-  size_t smem = (size_t)r.nraygeom * 12 * sizeof(float);
+  size_t smem = RAY_SMEM_BYTES(r);
   cudaFuncSetAttribute(lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   lidar_kernel<<<B->nenv, 128, smem, st>>>(r, B->nenv, B->dm.nsensordata, B->bufs.xpos, B->bufs.xquat, B->ray_xf, out_dev,
                                            out_dev ? nullptr : B->bufs.sensordata);
@@ -593,7 +718,7 @@ extern "C" int ss_batch_rays(ss_batch* B, int nray, const float* origin, const f
   cudaStream_t st = (cudaStream_t)s;
   if (prepare(B, st) != 0) return -1;
   const RayModel& r = B->model->rm;
-  size_t smem = (size_t)r.nraygeom * 12 * sizeof(float);
+  size_t smem = RAY_SMEM_BYTES(r);
   cudaFuncSetAttribute(rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   rays_kernel<<<B->nenv, 128, smem, st>>>(r, B->nenv, nray, B->ray_xf, origin, dir, groupmask, bodyexclude, dist, geom);
   B->launches++;
@@ -610,7 +735,7 @@ extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, u
   cudaStream_t st = (cudaStream_t)s;
   if (prepare(B, st) != 0) return -1;
   if (fovy <= 0) fovy = B->model->cam_fovy_host[cam];
-  size_t smem = (size_t)r.nraygeom * (12 * sizeof(float) + 2 * sizeof(int));
+  size_t smem = RAY_SMEM_BYTES(r) + (size_t)r.nraygeom * 2 * sizeof(int);
   cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, env_count), block(TILE, TILE);
   if (grid.z > 65535) return ss_fail("ss_batch_render: at most 65535 envs per call");

@@ -11,7 +11,8 @@ struct RayModel {
   const float *rg_pos, *rg_quat, *rg_size, *rg_rbound, *rg_shade; // shade: rgb, specular, shininess, emission (6)
   const int *rmesh_vertadr, *rmesh_faceadr, *rmesh_facenum, *rmesh_bvhadr;
   const float4* tri;        // 3 float4 per triangle: v0, e1, e2 (mesh frame), BVH leaf order
-  const float4* bvh;        // 2 float4 per node: (min.xyz, left|~firstTri), (max.xyz, right|count)
+  const float4* bvh;        // 4 float4 per internal node: children boxes + (refL, refR, cntL, cntR), see rays.cu
+  const float4* rg_rec;     // 4 float4 per ray-geom: (type, root ref, root count, body|group<<16), (rbound, size), lo, hi
   const int *cam_bodyid, *site_bodyid;
   const float *cam_pos, *cam_quat, *cam_fovy, *site_pos, *site_quat;
   const int *range_site;    // site id per rangefinder sensor
