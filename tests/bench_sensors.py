@@ -85,3 +85,18 @@ for cname in args.cams.split(","):
                       "rays_per_s": nenv * W * H / (med * 1e-3), "depth_cover_last_chunk": cover,
                       "roofline": {"bound": "hbm", "achieved": algo / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": algo / (med * 1e-3) / 1e9 / peak}}), flush=True)
+
+# BASELINE config 3: physics step + head RGB+depth render of every env, every mj_step
+cam = dm.name2id(engine.OBJ_CAMERA, "d435i_camera_rgb")
+fovy = float(A["cam_fovy"][cam])
+
+
+def cfg3_step():
+    B.step(1)
+    for e0 in range(0, nenv, chunk):
+        B.render(cam, W, H, fovy, rgb, depth, 10.0, env_begin=e0, env_count=min(chunk, nenv - e0))
+med, best = timed(cfg3_step, args.reps)
+print(json.dumps({"workload": "cfg3: physics step + %dx%d head RGB+depth render of every env each mj_step" % (W, H), "scene": args.scene,
+                  "nenv": nenv, "ms_per_step": med, "env_steps_per_s": nenv / (med * 1e-3),
+                  "roofline": {"bound": "hbm", "achieved": nenv * (W * H * 7 + 828) / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": nenv * (W * H * 7 + 828) / (med * 1e-3) / 1e9 / peak}}), flush=True)
