@@ -576,7 +576,8 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
   float4* srec = sm4;                                              // [nraygeom*4]
   float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);     // [nraygeom*12]
   int* list = (int*)(sxf + r.nraygeom * 12);                       // [nraygeom]
-  int* flag = list + r.nraygeom;                                   // [nraygeom]
+  int* flag = list + r.nraygeom;                                   // [nraygeom]; doubles as the depth-sorted list
+  float* skey = (float*)(flag + r.nraygeom);                       // [nraygeom] camera-space entry depth of the bounding sphere
   __shared__ int nlist;
   __shared__ float cam_eye[3], cam_R[9], focal;
   __shared__ float lvec[MAXLIGHT][4];   // world direction towards the light (w = 0) or its position (w = 1); slot 0 = headlight
@@ -631,6 +632,13 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
       bool keep = true;
       if (!((0x7 >> REC_GROUP(rec)) & 1)) keep = false;  // camera sees geom groups 0..2 (collision group 3 hidden)
       else if (REC_TYPE(rec) != GEOM_PLANE) keep = frustum_keeps<true>(rec, sxf + 12 * k, cam_eye, cam_R, pn, znear);
+      float key = -1.f;   // planes first: cheap, and their hit bounds everything behind them
+      if (keep && REC_TYPE(rec) != GEOM_PLANE) {
+        const float* T = sxf + 12 * k;
+        float dz = cam_R[2] * (T[0] - cam_eye[0]) + cam_R[5] * (T[1] - cam_eye[1]) + cam_R[8] * (T[2] - cam_eye[2]);
+        key = fmaxf(-dz - rec[1].x, 0.f);
+      }
+      skey[k] = key;
       flag[k] = keep;
     }
   }
@@ -647,6 +655,20 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
     if (tid == 0) nlist = n;
   }
   __syncthreads();
+  // front-to-back order (rank sort by entry depth, ties by geom id): near hits come first and prune the rest
+  {
+    const int nl = nlist;
+    int mine = -1, rank = 0;
+    if (tid < nl) {
+      mine = list[tid];
+      float km = skey[mine];
+      for (int j = 0; j < nl; j++) { int o2 = list[j]; float kj = skey[o2]; rank += (kj < km) || (kj == km && o2 < mine); }
+    }
+    __syncthreads();
+    if (mine >= 0) flag[rank] = mine;
+    __syncthreads();
+  }
+  const int* slist = flag;
   int u = tx * TILE + threadIdx.x, v = blockIdx.y * TILE + threadIdx.y;
   const bool inb = u < W && v < H;
   float dl[3] = {(u + 0.5f - 0.5f * W) / f, -(v + 0.5f - 0.5f * H) / f, -1.0f};
@@ -657,7 +679,7 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
     // (a second, per-warp culling level against 16 x 2 pixel strips was measured slower: 21.0 vs 19.7 ms)
     const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
     const int nl = nlist;
-    for (int i = 0; i < nl; i++) trace_one<false>(r, sxf, srec, list[i], cam_eye, dw, vv, znear, 0, -1, h);
+    for (int i = 0; i < nl; i++) trace_one<false>(r, sxf, srec, slist[i], cam_eye, dw, vv, znear, 0, -1, h);
   }
   if (inb) {
   float x = h.t;
@@ -769,7 +791,7 @@ extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, u
   cudaStream_t st = (cudaStream_t)s;
   if (prepare(B, st) != 0) return -1;
   if (fovy <= 0) fovy = B->model->cam_fovy_host[cam];
-  size_t smem = RAY_SMEM_BYTES(r) + (size_t)r.nraygeom * 2 * sizeof(int);
+  size_t smem = RAY_SMEM_BYTES(r) + (size_t)r.nraygeom * 3 * sizeof(int);
   cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((W + TILE * TILES_PER_CTA - 1) / (TILE * TILES_PER_CTA), (H + TILE - 1) / TILE, env_count), block(TILE, TILE);
   if (grid.z > 65535) return ss_fail("ss_batch_render: at most 65535 envs per call");
