@@ -235,8 +235,12 @@ class Scene:
         return sc
 
     @classmethod
-    def from_xml_string(cls, xml: str, base_dir: str = ".") -> "Scene":
+    def from_xml_string(cls, xml: str, base_dir: str = ".", replicate_override: dict | None = None) -> "Scene":
+        """``replicate_override`` maps the name of an element inside a <replicate> to ``(count, euler)``: the
+        benchmark's 1000-ray lidar re-spins the reference's 360-site ring without
+        editing the reference's stretch.xml."""
         sc = cls()
+        sc.replicate_override = dict(replicate_override or {})
         sc.base_dir = os.path.abspath(base_dir)
         root = ET.fromstring(xml)
         sc._expand_includes(root, sc.base_dir)
@@ -513,7 +517,11 @@ class Scene:
                 p, q = place(e.attrib)
                 self._parse_body_children(e, body_id, e.attrib.get("childclass", childclass), (p, q), suffix)
             elif t == "replicate":
-                a = e.attrib
+                a = dict(e.attrib)
+                for ch in e:
+                    ov = getattr(self, "replicate_override", {}).get(ch.attrib.get("name"))
+                    if ov:
+                        a["count"], a["euler"] = str(ov[0]), ov[1]
                 count = int(a["count"])
                 off = np.asarray(_floats(a.get("offset", "0 0 0"), 3))
                 rq = euler_quat([self._ang(x) for x in _floats(a.get("euler", "0 0 0"), 3)], self.eulerseq)

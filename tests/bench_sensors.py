@@ -26,7 +26,8 @@ ap.add_argument("--cams", default="d435i_camera_rgb")
 ap.add_argument("--skip-lidar", action="store_true")
 args = ap.parse_args()
 
-name = "stretch_empty_floor_render.ssm.z" if args.scene == "empty" else "stretch_default_scene_render.ssm.z"
+name = {"empty": "stretch_empty_floor_render.ssm.z", "default": "stretch_default_scene_render.ssm.z",
+        "kitchen": "stretch_kitchen_proxy_render.ssm.z"}[args.scene]
 raw = blob.read_bytes(os.path.join(os.path.dirname(bench.GOLDEN), name))
 A, _ = blob.unpack(raw)
 dm = engine.DeviceModel(raw, 0)
@@ -100,3 +101,21 @@ print(json.dumps({"workload": "cfg3: physics step + %dx%d head RGB+depth render 
                   "nenv": nenv, "ms_per_step": med, "env_steps_per_s": nenv / (med * 1e-3),
                   "roofline": {"bound": "hbm", "achieved": nenv * (W * H * 7 + 828) / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                "frac": nenv * (W * H * 7 + 828) / (med * 1e-3) / 1e9 / peak}}), flush=True)
+
+if args.scene == "kitchen":
+    # BASELINE config 4 (kitchen proxy): physics step + 1000-ray lidar + head 424x240 + wrist 480x270 RGB+depth each mj_step
+    cams = [(dm.name2id(engine.OBJ_CAMERA, "d435i_camera_rgb"), 424, 240, 42.0, 10.0), (dm.name2id(engine.OBJ_CAMERA, "d405_rgb"), 480, 270, 58.0, 1.0)]
+    bufs = [(torch.empty(chunk, h, w, 3, dtype=torch.uint8, device=dev), torch.empty(chunk, h, w, device=dev)) for _, w, h, _, _ in cams]
+    scan = torch.empty(nenv, dm.nrange, device=dev)
+
+    def cfg4_step():
+        B.step(1)
+        B.lidar(scan)
+        for (cid, w, h, fv, lim), (c, d) in zip(cams, bufs):
+            for e0 in range(0, nenv, chunk):
+                B.render(cid, w, h, fv, c, d, lim, env_begin=e0, env_count=min(chunk, nenv - e0))
+    med, best = timed(cfg4_step, args.reps)
+    algo = nenv * (828 + 4 * dm.nrange + 1200 + 7 * (424 * 240 + 480 * 270))
+    print(json.dumps({"workload": "cfg4 (kitchen proxy): physics step + %d-ray lidar + head 424x240 + wrist 480x270 RGB+depth each mj_step" % dm.nrange,
+                      "nenv": nenv, "ms_per_step": med, "env_steps_per_s": nenv / (med * 1e-3),
+                      "roofline": {"bound": "hbm", "achieved": algo / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (med * 1e-3) / 1e9 / peak}}), flush=True)

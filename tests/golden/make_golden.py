@@ -25,3 +25,6 @@ if __name__ == "__main__":
     m = scenes.compile_default_scene(with_render=True)
     blob.save(os.path.join(HERE, "stretch_default_scene_render.ssm.z"), m)
     print("render blobs: %d ray geoms, %d triangles" % (len(m.raygeom_id), len(m.rmesh_face)))
+    m = scenes.compile_kitchen_proxy(with_render=True, lidar_rays=1000)
+    blob.save(os.path.join(HERE, "stretch_kitchen_proxy_render.ssm.z"), m)
+    print("kitchen proxy:", m.sizes)

@@ -153,3 +153,82 @@ def test_default_scene_physics_forward_parity(scene):
     # 200 steps: objects fall on the table, robot homes; no env may blow up
     B.step(200); torch.cuda.synchronize()
     assert torch.isfinite(B.qpos).all() and int((B.env_flags & 1).max()) == 0
+
+
+# ----------------------------------------------------------------------------- BASELINE config 4 (kitchen proxy)
+@pytest.fixture(scope="module")
+def kitchen():
+    """stretch.xml inside the box fixtures of robocasa's one_wall_small layout + one free box, 1000-ray lidar
+    (stretch_mujoco_b200/scenes.py: KITCHEN_PROXY_XML; the real Robocasa assets are download-only)."""
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob, engine
+    raw = blob.read_bytes(os.path.join(GOLDEN, "stretch_kitchen_proxy_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    return dict(raw=raw, A=A, names=names, om=OracleModel(raw), dm=engine.DeviceModel(raw, 0))
+
+
+def test_kitchen_proxy_physics_lidar_and_cameras(kitchen):
+    from stretch_mujoco_b200 import engine
+    from stretch_mujoco_b200.mjcf import quat2mat, quat_mul
+    A, om, dm = kitchen["A"], kitchen["om"], kitchen["dm"]
+    assert dm.nv == 32 and dm.nrange == 1000
+    nenv = 4
+    B = engine.Batch(dm, nenv, debug=True, maxcon=32)
+    B.reset(key=0)
+    q = B.qpos.cpu().numpy().astype(np.float64)
+    q[1, 0:2] = [0.4, -0.3]; ang = 1.2; q[1, 3:7] = [np.cos(ang / 2), 0, 0, np.sin(ang / 2)]      # base moved / turned
+    q[2, 0:2] = [-0.5, 0.2]; ang = -2.4; q[2, 3:7] = [np.cos(ang / 2), 0, 0, np.sin(ang / 2)]
+    q[3, 9] = 0.9; q[3, 10:14] = 0.08
+    q[:, 29] = 0.968                                   # box settled 2 mm into the counter top (qpos0 has it exactly touching)
+    B.qpos.copy_(torch.tensor(q, dtype=torch.float32))
+    rng = np.random.default_rng(11)
+    B.qvel.copy_(torch.tensor(rng.normal(scale=0.02, size=(nenv, dm.nv)), dtype=torch.float32))
+    f = lambda t: t.cpu().numpy().astype(np.float64)
+    qpos, qvel, ctrl = f(B.qpos), f(B.qvel), f(B.ctrl)
+    B.forward(); torch.cuda.synchronize()
+    # physics: free box resting on the counter (box-box through MPR), nv = 32 register tile
+    om.set_options(enable_lidar=False)
+    o = om.forward(qpos, qvel, ctrl, None, maxcon=32, want=("M", "contact_geom", "ncon", "nefc", "qacc", "qacc_smooth"))
+    assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])
+    assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
+    M = B.dbg["M"].cpu().numpy()
+    assert np.abs(M - o["M"]).max() <= 1e-5 * np.abs(o["M"]).max()
+    qa = B.qacc.cpu().numpy()
+    rel = np.abs(qa - o["qacc"]).max(1) / (np.abs(o["qacc"]).max(1) + 1e-3)
+    assert np.median(rel) < 1e-3 and rel.max() < 2e-2, rel
+    # lidar: 1000 rays per env against the oracle (walls, counter, stove, tap, robot's own meshes)
+    dist = B.lidar().cpu().numpy()
+    xpos, xquat = f(B.xpos), f(B.xquat)
+    names = kitchen["names"][3]
+    sid = [names.index(f"lidar{i:04d}") for i in range(1000)]
+    b = A["site_bodyid"][sid[0]]
+    org = np.zeros((nenv, 1000, 3)); dr = np.zeros((nenv, 1000, 3))
+    for e in range(nenv):
+        Rb = quat2mat(xquat[e, b])
+        for i, s in enumerate(sid):
+            org[e, i] = xpos[e, b] + Rb @ A["site_pos"][s]
+            dr[e, i] = quat2mat(quat_mul(xquat[e, b], A["site_quat"][s]))[:, 2]
+    ref, _ = om.rays(xpos, xquat, org, dr, groupmask=0, bodyexclude=int(b))
+    ref = np.where(ref > 10.0, 10.0, ref)
+    dc, rc = np.where(dist < 0, 10.0, dist), np.where(ref < 0, 10.0, ref)
+    assert ((dc < 10.0) == (rc < 10.0)).mean() > 0.995
+    hit = (dc < 10.0) & (rc < 10.0)
+    assert hit.mean() > 0.6 and _frac_close(dc[hit], rc[hit], 1e-4) > 0.995
+    # env 0: robot at the origin, back wall plane y = 1.45 m in front of ... (kitchen body at y = 1.45): the ray
+    # pointing along world +y from the laser reads (1.45 - y_laser); rays are spaced 0.36 degrees
+    lp = xpos[0, b]
+    k = int(np.argmax(dr[0, :, 1]))
+    assert dist[0, k] == pytest.approx((1.45 - 0.65 - lp[1]) / dr[0, k, 1], abs=3e-3)    # counter front face (y = 1.45 - 0.65)
+    # cameras at their native parity sizes: head d435i 424x240 (depth limit 10 m), wrist d405 480x270 (1 m)
+    for cam_name, W, H, fovy in (("d435i_camera_depth", 424, 240, 42.0), ("d405_rgb", 480, 270, 58.0)):
+        cam = dm.name2id(engine.OBJ_CAMERA, cam_name)
+        rgb = torch.zeros(nenv, H, W, 3, dtype=torch.uint8, device="cuda"); depth = torch.zeros(nenv, H, W, device="cuda")
+        B.render(cam, W, H, fovy, rgb, depth)
+        torch.cuda.synchronize()
+        rrgb, rdepth = om.render(xpos, xquat, cam, W, H, fovy)
+        assert _frac_close(depth.cpu().numpy(), rdepth, 1e-4) > 0.995
+        assert (np.abs(rgb.cpu().numpy().astype(int) - rrgb.astype(int)).max(axis=-1) <= 2).mean() > 0.99
+    # 300 steps with the home command: nothing blows up, the box stays on the counter
+    B.step(300); torch.cuda.synchronize()
+    assert torch.isfinite(B.qpos).all() and int((B.env_flags & 1).max()) == 0
+    assert float(B.qpos[0, 29]) > 0.9
