@@ -34,45 +34,33 @@ extern "C" const char* ss_version(void) { return "stretchsim 0.1.0 (sm_100a)"; }
 
 extern "C" __global__ void ss_physics_kernel(DevModel m, StepArgs a);
 
-// Env visiting order for the next physics launch: counting sort of the envs by the cost they
-// reported in the previous launch (Newton iterations + narrowphase queries), heaviest first.
-// Costs change slowly from one control period to the next, so consecutive slots hold envs of
-// similar cost.  The order only affects which warp simulates which env, never the results.
-__global__ void schedule_kernel(int nenv, const int32_t* __restrict__ cost, int nsteps_prev, int32_t* __restrict__ order,
+// Env visiting order for the next physics launch: counting sort of the envs by the cost they reported in
+// the LAST step of the previous launch (Newton iterations + narrowphase queries), heaviest first.  An env's
+// cost is persistent over a few steps (step-to-step correlation 0.74) but not over a control period, so
+// long rollouts are cut into short launches (ss_batch_step) and re-sorted in between.  The order only
+// affects which warp simulates which env, never the results.
+__global__ void schedule_kernel(int nenv, const int32_t* __restrict__ cost, int mode, int32_t* __restrict__ order,
                                 int32_t* __restrict__ work_counter) {
   __shared__ int hist[256], start[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  if (nsteps_prev < 0) {  // SS_NOSORT=1: identity order (A/B knob)
+  if (threadIdx.x == 0) *work_counter = 0;
+  if (mode < 0) {  // SS_NOSORT=1: identity order (A/B knob)
     for (int e = threadIdx.x; e < nenv; e += blockDim.x) order[e] = e;
-    if (threadIdx.x == 0) *work_counter = 0;
     return;
   }
-  int scale = nsteps_prev > 0 ? nsteps_prev : 1;
-  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&hist[255 - min(255, 4 * cost[e] / scale)], 1);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int b = 0; b < 256; b++) { start[b] = acc; acc += hist[b]; }
-    *work_counter = 0;
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) atomicAdd(&hist[255 - min(255, 4 * cost[e])], 1);
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 buckets by one warp (8 buckets per lane)
+    int v[8], sum = 0;
+    for (int k = 0; k < 8; k++) { v[k] = hist[threadIdx.x * 8 + k]; sum += v[k]; }
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    int acc = incl - sum;
+    for (int k = 0; k < 8; k++) { start[threadIdx.x * 8 + k] = acc; acc += v[k]; }
   }
   __syncthreads();
-  // stable within a bucket: each warp-sized chunk of envs is placed in env order
-  for (int base = 0; base < nenv; base += blockDim.x) {
-    int e = base + threadIdx.x;
-    int b = e < nenv ? 255 - min(255, 4 * cost[e] / scale) : -1;
-    for (int w = 0; w < (int)blockDim.x / 32; w++) {
-      if ((int)threadIdx.x / 32 == w && b >= 0) {
-        unsigned peers = __match_any_sync(__activemask(), b);
-        int rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
-        int leader = __ffs(peers) - 1, pos = 0;
-        if ((int)(threadIdx.x & 31) == leader) pos = atomicAdd(&start[b], __popc(peers));
-        pos = __shfl_sync(peers, pos, leader);
-        order[pos + rank] = e;
-      }
-      __syncthreads();
-    }
-  }
+  for (int e = threadIdx.x; e < nenv; e += blockDim.x) order[atomicAdd(&start[255 - min(255, 4 * cost[e])], 1)] = e;
 }
 
 // ----------------------------------------------------------------------------- device upload helpers
@@ -422,7 +410,9 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
     ss_batch_free(B);
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  B->prev_nsteps = 1;
+  B->steps_per_launch = 2;   // measured: 50 -> 56.0, 10 -> 54.7, 5 -> 53.9, 2 -> 53.2, 1 -> 53.6 ms per 50 steps x 4096 envs
+  if (const char* e = getenv("SS_CHUNK")) B->steps_per_launch = std::max(1, atoi(e));
+  B->nosort = getenv("SS_NOSORT") != nullptr;
   *out = B;
   return 0;
 }
@@ -461,10 +451,14 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   B->dm.tolerance = B->model->dm.tolerance;
   size_t smem = B->pack_bytes + B->warps_per_block * B->smem_per_env;
   a.order = B->order; a.cost = B->cost; a.work_counter = B->work_counter;
-  schedule_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(B->nenv, B->cost, getenv("SS_NOSORT") ? -1 : B->prev_nsteps, B->order, B->work_counter);
-  if (!forward_only) B->prev_nsteps = nsteps;
-  ss_physics_kernel<<<B->grid, B->warps_per_block * 32, smem, (cudaStream_t)stream>>>(B->dm, a);
-  B->launches += 2;
+  // short launches, re-sorted in between (see schedule_kernel); observations come from the last one
+  int chunk = forward_only ? 1 : B->steps_per_launch;
+  for (int done = 0; done < nsteps; done += chunk) {
+    a.nsteps = std::min(chunk, nsteps - done);
+    schedule_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(B->nenv, B->cost, B->nosort ? -1 : 0, B->order, B->work_counter);
+    ss_physics_kernel<<<B->grid, B->warps_per_block * 32, smem, (cudaStream_t)stream>>>(B->dm, a);
+    B->launches += 2;
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }

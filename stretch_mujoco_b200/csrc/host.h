@@ -32,7 +32,8 @@ struct ss_batch {
   size_t smem_per_env, pack_bytes;
   int warps_per_block, grid, sync_level, group_warps;
   long launches;
-  int prev_nsteps = 1;
+  int steps_per_launch = 2;   // long rollouts are cut into launches of this many steps, re-sorted in between
+  bool nosort = false;
   int32_t *order = nullptr, *cost = nullptr, *work_counter = nullptr;  // cost-sorted env schedule (api.cu)
   float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
 };
