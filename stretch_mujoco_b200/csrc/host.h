@@ -23,6 +23,7 @@ struct ss_model {
   std::vector<void*> dev_allocs;
 };
 
+#define SS_MAXSETS 4
 struct ss_batch {
   const ss_model* model;
   int nenv;
@@ -34,6 +35,9 @@ struct ss_batch {
   long launches;
   int steps_per_launch = 2;   // long rollouts are cut into launches of this many steps, re-sorted in between
   bool nosort = false;
+  int nsets = 1;               // env sets with their own launch chains on side streams (tail overlap)
+  cudaStream_t side[SS_MAXSETS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[SS_MAXSETS] = {};
   int32_t *order = nullptr, *cost = nullptr, *work_counter = nullptr;  // cost-sorted env schedule (api.cu)
   float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
 };

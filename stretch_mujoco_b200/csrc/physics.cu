@@ -1774,6 +1774,11 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
     bool active = slot < a.nenv;
     int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
     int cost = 0;
+    if (a.sync_level & 96) {   // debug: scrub the env slice (32: zeros, 64: NaNs) to expose reads of stale shared memory
+      float fill = (a.sync_level & 64) ? __int_as_float(0x7fc00000) : 0.f;
+      _Pragma("unroll 1") for (int i = lane; i < o.total; i += 32) S[i] = fill;
+      __syncwarp();
+    }
     _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
     _Pragma("unroll 1") for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];

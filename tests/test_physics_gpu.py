@@ -248,3 +248,28 @@ def test_status_and_commands_follow_reference_semantics(gpu, arrays_E):
     assert np.allclose(sim.batch.ctrl[:, 0:2].cpu().numpy(), 0.0)
     sim.stop()
     assert not sim.is_running()
+
+
+def test_scheduling_does_not_leak_into_results(gpu, arrays_E, monkeypatch):
+    """The launch policy (cost-sorted work queue, 2-step launches, env sets on side streams) only decides
+    which warp simulates which env and when: a batch stepped with the policy switched off (one 50-step
+    launch, identity order, one set) must stay bit-identical to the default one over a random-ctrl rollout."""
+    import bench
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    nenv = 2048
+    B1 = engine.Batch(gpu, nenv)
+    for k, v in (("SS_SETS", "1"), ("SS_CHUNK", "50"), ("SS_NOSORT", "1")):
+        monkeypatch.setenv(k, v)
+    B2 = engine.Batch(gpu, nenv)
+    dev = B1.qpos.device
+    lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev)
+    hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
+    for p in range(5):
+        c = bench.ctrl_torch(0, 0, nenv, p, lo, hi, dev)
+        B1.ctrl.copy_(c); B2.ctrl.copy_(c)
+        B1.step(50); B2.step(50)
+        torch.cuda.synchronize()
+        assert torch.equal(B1.qpos, B2.qpos) and torch.equal(B1.qvel, B2.qvel) and torch.equal(B1.qacc_warmstart, B2.qacc_warmstart)
+        assert torch.equal(B1.xpos, B2.xpos) and torch.equal(B1.contact_geom, B2.contact_geom) and torch.equal(B1.time, B2.time)
+    assert B1.launches > B2.launches
