@@ -252,7 +252,7 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum over the launches of one bench step (committed ncu capture)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "physics_traffic.json")))
         if nenv == 4096:
@@ -274,11 +274,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "ss_physics_kernel", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * nenv * MJ_STEPS_PER_STEP,
+                         "algorithmic_bytes_per_step": ALGO_BYTES_PER_ENV_STEP * nenv * MJ_STEPS_PER_STEP,
+                         "launches_per_step": int(launches) // K,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "note": "physics is instruction-issue/latency bound, not HBM bound: 828 algorithmic B per env-step "
-                                 "(SURVEY.md 8(d)); measured DRAM traffic is below that because the state stays in shared "
-                                 "memory for the 50 steps of a launch; see profiles/physics_r1.md"},
+                         "note": "per bench step (= launches_per_step launches: 2-step launches of two env sets, each preceded by "
+                                 "schedule_kernel); physics is instruction-supply/latency bound, not HBM bound: 828 "
+                                 "algorithmic B per env-step (SURVEY.md 8(d)); measured DRAM traffic is below that because "
+                                 "the working set lives in shared memory and the state round trips stay in L2; see "
+                                 "profiles/physics_r1.md"},
             "rollout_metrics": {"env_steps": float(gathered[:, 0].sum()), "sum_abs_qpos": float(gathered[:, 2].sum()),
                                 "contacts_last_step": float(gathered[:, 3].sum()), "envs_reset": float(gathered[:, 4].sum())}}
     if world == 1 and not args.no_cpu:
