@@ -453,7 +453,8 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   StepArgs a;
   memset(&a, 0, sizeof(a));
   const ss_buffers& f = B->bufs;
-  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level; a.group_warps = B->group_warps;
+  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level; a.group_warps = B->group_warps; a.cost_w = 8;
+  if (const char* e = getenv("SS_COSTW")) a.cost_w = atoi(e);
   a.qpos = f.qpos; a.qvel = f.qvel; a.warm = f.qacc_warmstart; a.time = f.time; a.ctrl = f.ctrl;
   a.xpos = f.xpos; a.xquat = f.xquat; a.act_length = f.act_length; a.act_velocity = f.act_velocity;
   a.sensordata = f.sensordata; a.qacc = f.qacc; a.ncon = f.ncon; a.contact_geom = f.contact_geom;

@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 struct StepArgs {
-  int nenv, nsteps, forward_only, sync_level, group_warps;
+  int nenv, nsteps, forward_only, sync_level, group_warps, cost_w;
   float *qpos, *qvel, *warm, *time, *ctrl;
   float *xpos, *xquat, *act_length, *act_velocity, *sensordata, *qacc;
   int32_t *ncon, *contact_geom;

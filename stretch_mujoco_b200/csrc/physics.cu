@@ -1817,7 +1817,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, active, ssync);
         else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
         fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
-        cost = 8 * fi.iter + fi.nnarrow;   // last step's cost: the predictor for the next launch's schedule
+        cost = a.cost_w * fi.iter + fi.nnarrow;   // last step's cost: the predictor for the next launch's schedule
         if (active) _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();
         }

@@ -119,3 +119,35 @@ def test_lidar_sensor_names(model_E):
     # enums/stretch_sensors.py:33-41 expects base_lidar000 .. base_lidar359
     assert names[0] == "base_gyro" and names[1] == "base_accel"
     assert names[2:] == [f"base_lidar{i:03d}" for i in range(360)]
+
+
+def test_kitchen_proxy_golden_layout():
+    """BASELINE config 4 stand-in (scenes.KITCHEN_PROXY_XML): robot + static box fixtures + one free box, lidar
+    ring re-spun at 1000 rays through the loader's replicate override."""
+    import os
+    from conftest import GOLDEN
+    from stretch_mujoco_b200 import blob
+    A, names = blob.unpack(blob.read_bytes(os.path.join(GOLDEN, "stretch_kitchen_proxy_render.ssm.z")))
+    assert len(A["qpos0"]) == 34 and len(A["dof_bodyid"]) == 32                 # 27 + 7, 26 + 6
+    snames = names[3]
+    assert snames.count("lidar0000") == 1 and "lidar0999" in snames and "lidar1000" not in snames
+    sid = [snames.index(f"lidar{i:04d}") for i in (0, 250, 500)]
+    from stretch_mujoco_b200.mjcf import quat2mat
+    z = [quat2mat(A["site_quat"][s])[:, 2] for s in sid]                        # ray direction = site +z
+    assert np.allclose(z[0], [1, 0, 0], atol=1e-9) and np.allclose(z[1], [0, 1, 0], atol=1e-6) and np.allclose(z[2], [-1, 0, 0], atol=1e-6)
+    gnames = names[2]
+    for g in ("wall", "wall_left", "wall_right", "counter_main", "stove", "counter_right", "floor"):
+        assert g in gnames
+    st = np.asarray(A["sensor_type"])
+    assert (st == 2).sum() == 1000 and len(A["raygeom_id"]) > 80
+
+
+@needs_ref
+def test_kitchen_proxy_golden_matches_fresh_compile():
+    import os
+    from conftest import GOLDEN
+    from stretch_mujoco_b200 import blob, scenes
+    A, _ = blob.unpack(blob.read_bytes(os.path.join(GOLDEN, "stretch_kitchen_proxy_render.ssm.z")))
+    m = scenes.compile_kitchen_proxy(with_render=True, lidar_rays=1000)
+    for k in ("qpos0", "body_mass", "geom_size", "site_quat", "pair_geom1", "pair_geom2", "rmesh_face"):
+        assert np.array_equal(np.asarray(m.arrays[k]), A[k]), k
