@@ -411,7 +411,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
     ss_batch_free(B);
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  B->steps_per_launch = 2;   // measured: 50 -> 56.0, 10 -> 54.7, 5 -> 53.9, 2 -> 53.2, 1 -> 53.6 ms per 50 steps x 4096 envs
+  B->steps_per_launch = 1;   // measured (1 set): 50 -> 56.0, 10 -> 54.7, 5 -> 53.9, 2 -> 53.2, 1 -> 53.6 ms per 50 steps x 4096 envs; (2 sets): 2 -> 48.9, 1 -> 47.9
   if (const char* e = getenv("SS_CHUNK")) B->steps_per_launch = std::max(1, atoi(e));
   B->nosort = getenv("SS_NOSORT") != nullptr;
   B->nsets = nenv >= 8 * sms ? 2 : 1;   // measured at 4096 envs: 1 set 53.2 ms, 2 sets 48.9 ms, 4 sets 48.8 ms per 50 steps

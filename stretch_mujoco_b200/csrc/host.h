@@ -33,7 +33,7 @@ struct ss_batch {
   size_t smem_per_env, pack_bytes;
   int warps_per_block, grid, sync_level, group_warps;
   long launches;
-  int steps_per_launch = 2;   // long rollouts are cut into launches of this many steps, re-sorted in between
+  int steps_per_launch = 1;   // long rollouts are cut into launches of this many steps, re-sorted in between
   bool nosort = false;
   int nsets = 1;               // env sets with their own launch chains on side streams (tail overlap)
   cudaStream_t side[SS_MAXSETS] = {};
