@@ -7,8 +7,10 @@
  * Conventions: plain pointers and sizes, no exceptions; every function returns 0 on success
  * and a negative code on error with a thread-local message in ss_last_error().  All per-env
  * device arrays are env-major `[nenv, n]`, fp32 (int32 for indices), owned by the CALLER
- * (torch allocates them and passes data_ptr()).  Kernels run on the caller's stream; no
- * function synchronises the device.
+ * (torch allocates them and passes data_ptr()).  Work is ordered by the caller's stream: kernels run on it, or
+ * (ss_batch_step on large batches) on library-owned side streams that are forked from and joined back into it with
+ * events, so that everything enqueued on the caller's stream before / after a call happens before / after the
+ * call's work.  No function synchronises the device or blocks the host.
  */
 #ifndef STRETCHSIM_H
 #define STRETCHSIM_H
@@ -77,8 +79,10 @@ void ss_batch_free(ss_batch*);
 /* qpos <- key_qpos[key] (or qpos0 when key<0), qvel = warmstart = time = 0, ctrl <- key_ctrl
  * for envs whose mask is non-zero (NULL mask = all). */
 int ss_batch_reset(ss_batch*, const int32_t* env_mask_dev, int key_id, ss_stream);
-/* nsteps x mj_step (stretch_mujoco/mujoco_server.py:378): S1..S10 of SURVEY.md §8(a) fused
- * in one persistent kernel, state held on chip between steps; ctrl is read once per call. */
+/* nsteps x mj_step (stretch_mujoco/mujoco_server.py:378): S1..S10 of SURVEY.md §8(a) fused in one persistent
+ * kernel per launch.  The call is cut into short launches whose env->warp assignment is re-sorted by the cost each
+ * env reported in its last step (csrc/api.cu:launch_physics); results do not depend on that policy.  ctrl is
+ * read at every step from the ctrl buffer as it is when the call's work executes. */
 int ss_batch_step(ss_batch*, int nsteps, ss_stream);
 /* forward dynamics only (mj_forward): fills the output buffers, leaves the state untouched */
 int ss_batch_forward(ss_batch*, ss_stream);
