@@ -950,19 +950,20 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
 
 // analytic plane-vs-primitive routines and MPR for the rest; fills up to 4 contacts
 __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, float margin, int so, int lane) {
-  // result record in shared memory (every lane writes the same values): count, normal[3], dist[4], pos[4][3]
+  // result record in shared memory, written by lane 0 (the computation is warp-uniform): count, normal[3], dist[4], pos[4][3]
+  const bool w0 = lane == 0;
   int& OC = reinterpret_cast<int&>(smem[so]);
   float *ON = smem + so + 1, *OD = smem + so + 4, *OP = smem + so + 8;
-  OC = 0;
+  if (w0) OC = 0;
   if (A.type == GEOM_PLANE) {
     float n[3] = {A.mat[2], A.mat[5], A.mat[8]};
-    ON[0] = n[0]; ON[1] = n[1]; ON[2] = n[2];
+    if (w0) ON[0] = n[0]; if (w0) ON[1] = n[1]; if (w0) ON[2] = n[2];
     float dif[3] = {B.pos[0] - A.pos[0], B.pos[1] - A.pos[1], B.pos[2] - A.pos[2]};
     if (B.type == GEOM_SPHERE) {
       float r = B.size[0], dist = dot3(dif, n) - r;
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) OP[3 * 0 + k] = B.pos[k] - n[k] * (r + 0.5f * dist);
-      OD[0] = dist; OC = 1;
+      for (int k = 0; k < 3; k++) if (w0) OP[3 * 0 + k] = B.pos[k] - n[k] * (r + 0.5f * dist);
+      if (w0) OD[0] = dist; if (w0) OC = 1;
     } else if (B.type == GEOM_CYLINDER) {
       float axis[3] = {B.mat[2], B.mat[5], B.mat[8]}, vec[3];
       float r = B.size[0], h = B.size[1];
@@ -978,12 +979,12 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
       float dist = dist0 + prjaxis + prjvec;
       if (dist > margin) return;
       int c = 0;
-      for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
-      OD[c++] = dist;
+      for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
+      { if (w0) OD[c] = dist; c++; }
       dist = dist0 - prjaxis + prjvec;
       if (dist <= margin) {
-        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
-        OD[c++] = dist;
+        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
+        { if (w0) OD[c] = dist; c++; }
       }
       float prjvec1 = -prjvec * 0.5f;
       dist = dist0 + prjaxis + prjvec1;
@@ -992,14 +993,14 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         cross3(vec1, vec, axis); normalize3(vec1);
         float s = r * 0.8660254037844386f;
         vec1[0] *= s; vec1[1] *= s; vec1[2] *= s;
-        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-        OD[c++] = dist;
+        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+        { if (w0) OD[c] = dist; c++; }
         if (c < 4) {
-          for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-          OD[c++] = dist;
+          for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
+          { if (w0) OD[c] = dist; c++; }
         }
       }
-      OC = c;
+      if (w0) OC = c;
     } else if (B.type == GEOM_BOX) {
       float dist = dot3(dif, n);
       int c = 0;
@@ -1010,26 +1011,26 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         float ldist = dot3(n, vec);
         if (dist + ldist > margin || ldist > 0) continue;
         float cd = dist + ldist;
-        for (int k = 0; k < 3; k++) OP[3 * c + k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
-        OD[c++] = cd;
+        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
+        { if (w0) OD[c] = cd; c++; }
       }
-      OC = c;
+      if (w0) OC = c;
     } else if (B.type == GEOM_MESH) {
       float nd[3] = {-n[0], -n[1], -n[2]}, s[3];
       support(B, nd, s, lane);
       float d3[3] = {s[0] - A.pos[0], s[1] - A.pos[1], s[2] - A.pos[2]};
       float dist = dot3(d3, n);
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) OP[3 * 0 + k] = s[k] - n[k] * 0.5f * dist;
-      OD[0] = dist; OC = 1;
+      for (int k = 0; k < 3; k++) if (w0) OP[3 * 0 + k] = s[k] - n[k] * 0.5f * dist;
+      if (w0) OD[0] = dist; if (w0) OC = 1;
     }
   } else {
     float depth, dir[3], pos[3];
     if (!mpr_penetration(A, B, &depth, dir, pos, lane)) return;
     if (dot3(dir, dir) < 0.5f) return;
-    ON[0] = dir[0]; ON[1] = dir[1]; ON[2] = dir[2];
-    OP[3 * 0 + 0] = pos[0]; OP[3 * 0 + 1] = pos[1]; OP[3 * 0 + 2] = pos[2];
-    OD[0] = -depth; OC = 1;
+    if (w0) ON[0] = dir[0]; if (w0) ON[1] = dir[1]; if (w0) ON[2] = dir[2];
+    if (w0) OP[3 * 0 + 0] = pos[0]; if (w0) OP[3 * 0 + 1] = pos[1]; if (w0) OP[3 * 0 + 2] = pos[2];
+    if (w0) OD[0] = -depth; if (w0) OC = 1;
   }
 }
 
