@@ -115,3 +115,28 @@ def test_solver_optimality(oracle_E, settled_home_E):
     assert np.allclose(lhs, o["qfrc_constraint"][0], atol=1e-6 * max(1.0, np.abs(lhs).max()))
     n = o["nefc"][0]
     assert np.allclose(o["efc_J"][0, :n].T @ o["efc_force"][0, :n], o["qfrc_constraint"][0], atol=1e-9)
+
+
+def test_solver_optimality_on_random_rollout_states(oracle_E, arrays_E):
+    """Regression for the line-search defect the device comparison exposed: on states of the
+    bench workload (limits, self-contact, sliding wheels) the Newton solve must end at a stationary point,
+    M qacc - qfrc_smooth - J^T f = 0, in EVERY env -- a premature stop showed up as residuals of 200-650."""
+    import bench
+    A, _ = arrays_E
+    om = oracle_E
+    om.set_options(enable_lidar=False)
+    nenv = 256
+    lo, hi = A["actuator_ctrlrange"][:, 0].copy(), A["actuator_ctrlrange"][:, 1].copy()
+    q = np.tile(A["qpos0"], (nenv, 1)); v = np.zeros((nenv, om.nv)); w = np.zeros((nenv, om.nv)); t = np.zeros(nenv)
+    worst = 0.0
+    for p in range(3):
+        c = bench.ctrl_np(0, 0, nenv, p, lo, hi)
+        for chunk in (7, 43):
+            om.step(q, v, c, w, t, nsteps=chunk)
+            o = om.forward(q, v, c, w, want=("qacc", "M", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qfrc_constraint", "solver_iter", "flags"))
+            smooth = o["qfrc_passive"] - o["qfrc_bias"] + o["qfrc_actuator"]
+            r = np.einsum("eij,ej->ei", o["M"], o["qacc"]) - smooth - o["qfrc_constraint"]
+            scale = np.maximum(np.abs(smooth).max(1), 1.0)
+            worst = max(worst, float((np.abs(r).max(1) / scale).max()))
+            assert o["solver_iter"].max() < 50
+    assert worst < 1e-5, worst
