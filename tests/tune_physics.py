@@ -7,7 +7,7 @@ from stretch_mujoco_b200 import engine, blob
 raw = open(bench.GOLDEN, "rb").read()
 A, _ = blob.unpack(raw)
 dm = engine.DeviceModel(raw, 0)
-nenv = 4096
+nenv = int(os.environ.get("NENV", 4096))
 B = engine.Batch(dm, nenv)
 dev = B.qpos.device
 lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev); hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
