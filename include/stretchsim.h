@@ -137,6 +137,12 @@ int ss_batch_rays(ss_batch*, int nray, const float* origin_dev, const float* dir
  * depth_limit > 0 applies utils.limit_depth_distance (stretch_mujoco/utils.py:87-91). */
 int ss_batch_render(ss_batch*, int cam_id, int W, int H, float fovy_deg, uint8_t* rgb_dev, float* depth_dev,
                     float depth_limit, int env_begin, int env_count, ss_stream);
+/* same, with the client-side post-processing of StatusStretchCameras.get_camera_data
+ * (stretch_mujoco/datamodels/status_stretch_camera.py:47-82) fused into the kernel's epilogue:
+ * rot90 = k of numpy.rot90 (-1 for the d435i cameras, +1 for the nav camera, 0 none; rotated outputs are
+ * [nenv,W,H,3] / [nenv,W,H]), bgr != 0 = cv2.COLOR_RGB2BGR channel order. */
+int ss_batch_render_post(ss_batch*, int cam_id, int W, int H, float fovy_deg, uint8_t* rgb_dev, float* depth_dev,
+                         float depth_limit, int env_begin, int env_count, int rot90, int bgr, ss_stream);
 
 const char* ss_last_error(void);
 const char* ss_version(void);

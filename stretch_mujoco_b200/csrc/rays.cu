@@ -571,7 +571,7 @@ __global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restr
 __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env_begin, int cam, int W, int H, float fovy_deg,
                                                              const float* __restrict__ xpos, const float* __restrict__ xquat,
                                                              const float* __restrict__ xf_all, uint8_t* __restrict__ rgb,
-                                                             float* __restrict__ depth, float depth_limit) {
+                                                             float* __restrict__ depth, float depth_limit, int post) {
   extern __shared__ float4 sm4[];
   float4* srec = sm4;                                              // [nraygeom*4]
   float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);     // [nraygeom*12]
@@ -684,7 +684,13 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
   if (inb) {
   float x = h.t;
   if (x < 0 || x > zfar) { x = zfar; h.k = -1; }
-  size_t pix = ((size_t)le * H + v) * W + u;
+  // client-side post-processing of the reference fused into the epilogue (status_stretch_camera.py:47-82):
+  // post bits 1-2: 0 camera orientation, 1 = np.rot90(img, 1) (nav camera), 2 = np.rot90(img, -1) (d435i);
+  // bit 0: BGR channel order (cv2.COLOR_RGB2BGR).  Rotated images are [nenv, W, H(,3)].
+  const int rot = (post >> 1) & 3;
+  size_t pix = rot == 0 ? ((size_t)le * H + v) * W + u
+             : rot == 1 ? ((size_t)le * W + (W - 1 - u)) * H + v
+                        : ((size_t)le * W + u) * H + (H - 1 - v);
   if (depth) depth[pix] = (depth_limit > 0 && x > depth_limit) ? 0.f : x;   // utils.limit_depth_distance
   if (rgb) {
     float col[3];
@@ -730,7 +736,7 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
       }
     }
     uint8_t* px = rgb + 3 * pix;
-    for (int a = 0; a < 3; a++) px[a] = (uint8_t)(fminf(fmaxf(col[a], 0.f), 1.f) * 255.0f + 0.5f);
+    for (int a = 0; a < 3; a++) px[(post & 1) ? 2 - a : a] = (uint8_t)(fminf(fmaxf(col[a], 0.f), 1.f) * 255.0f + 0.5f);
   }
   }
   __syncthreads();   // list / flag are rebuilt for the next tile
@@ -782,9 +788,17 @@ extern "C" int ss_batch_rays(ss_batch* B, int nray, const float* origin, const f
   return 0;
 }
 
+extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fovy, uint8_t* rgb, float* depth, float depth_limit,
+                                    int env_begin, int env_count, int rot90, int bgr, ss_stream s);
 extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, uint8_t* rgb, float* depth, float depth_limit,
                                int env_begin, int env_count, ss_stream s) {
+  return ss_batch_render_post(B, cam, W, H, fovy, rgb, depth, depth_limit, env_begin, env_count, 0, 0, s);
+}
+extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fovy, uint8_t* rgb, float* depth, float depth_limit,
+                                    int env_begin, int env_count, int rot90, int bgr, ss_stream s) {
   if (!B || W <= 0 || H <= 0 || (!rgb && !depth)) return ss_fail("ss_batch_render: bad argument");
+  if (rot90 < -1 || rot90 > 1) return ss_fail("ss_batch_render_post: rot90 must be -1, 0 or 1 (numpy.rot90 k)");
+  int post = (bgr ? 1 : 0) | ((rot90 == 1 ? 1 : rot90 == -1 ? 2 : 0) << 1);
   const RayModel& r = B->model->rm;
   if (r.present && (cam < 0 || cam >= r.ncam)) return ss_fail("ss_batch_render: camera %d out of range", cam);
   if (env_begin < 0 || env_count <= 0 || env_begin + env_count > B->nenv) return ss_fail("ss_batch_render: env range out of bounds");
@@ -795,7 +809,7 @@ extern "C" int ss_batch_render(ss_batch* B, int cam, int W, int H, float fovy, u
   cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((W + TILE * TILES_PER_CTA - 1) / (TILE * TILES_PER_CTA), (H + TILE - 1) / TILE, env_count), block(TILE, TILE);
   if (grid.z > 65535) return ss_fail("ss_batch_render: at most 65535 envs per call");
-  render_kernel<<<grid, block, smem, st>>>(r, env_begin, cam, W, H, fovy, B->bufs.xpos, B->bufs.xquat, B->ray_xf, rgb, depth, depth_limit);
+  render_kernel<<<grid, block, smem, st>>>(r, env_begin, cam, W, H, fovy, B->bufs.xpos, B->bufs.xquat, B->ray_xf, rgb, depth, depth_limit, post);
   B->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -23,7 +23,7 @@ EXPORTS = [
     "ss_model_load_blob", "ss_model_free", "ss_model_dims", "ss_name2id", "ss_id2name", "ss_model_get", "ss_model_set",
     "ss_batch_create", "ss_batch_free", "ss_batch_reset", "ss_batch_step", "ss_batch_forward", "ss_batch_launch_count",
     "ss_batch_set_debug", "ss_batch_pull_status", "ss_batch_apply_commands", "ss_batch_lidar",
-    "ss_model_num_rangefinders", "ss_batch_rays", "ss_batch_render", "ss_last_error", "ss_version",
+    "ss_model_num_rangefinders", "ss_batch_rays", "ss_batch_render", "ss_batch_render_post", "ss_last_error", "ss_version",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
                                     C.c_void_p]
         L.ss_batch_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
                                       C.c_int, C.c_int, C.c_void_p]
+        L.ss_batch_render_post.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -231,12 +233,14 @@ class Batch:
         return dist, geom
 
     def render(self, cam_id: int, W: int, H: int, fovy: float, rgb=None, depth=None, depth_limit: float = 0.0,
-               env_begin: int = 0, env_count: int | None = None):
+               env_begin: int = 0, env_count: int | None = None, rot90: int = 0, bgr: bool = False):
+        """rot90 / bgr: the reference's client-side np.rot90(img, k) / RGB->BGR fused into the kernel; with
+        rot90 != 0 the output tensors are [n, W, H(, 3)]."""
         n = self.nenv - env_begin if env_count is None else env_count
-        _check(lib().ss_batch_render(self._h, cam_id, W, H, float(fovy),
-                                     None if rgb is None else C.c_void_p(rgb.data_ptr()),
-                                     None if depth is None else C.c_void_p(depth.data_ptr()), float(depth_limit),
-                                     env_begin, n, _stream()))
+        _check(lib().ss_batch_render_post(self._h, cam_id, W, H, float(fovy),
+                                          None if rgb is None else C.c_void_p(rgb.data_ptr()),
+                                          None if depth is None else C.c_void_p(depth.data_ptr()), float(depth_limit),
+                                          env_begin, n, int(rot90), int(bool(bgr)), _stream()))
         return rgb, depth
 
     @property

@@ -208,10 +208,14 @@ class StretchMujocoSimulator:
         return out
 
     def pull_camera_data(self, cameras: list | None = None, width: int | None = None, height: int | None = None,
-                         env_begin: int = 0, env_count: int | None = None) -> dict:
+                         env_begin: int = 0, env_count: int | None = None, auto_rotate: bool = False,
+                         auto_correct_rgb: bool = False) -> dict:
         """{StretchCameras: tensor}: RGB uint8 [n,H,W,3] or depth float32 [n,H,W] with the depth
-        limit applied (camera_manager.py:127-143, utils.py:87-91).  Images are in camera
-        orientation (the reference's client-side rot90 for d435i/nav is not applied)."""
+        limit applied (camera_manager.py:127-143, utils.py:87-91).  By default images are in camera
+        orientation, RGB order (what the reference's server produces).  `auto_rotate` / `auto_correct_rgb`
+        apply what StatusStretchCameras.get_camera_data does on the client
+        (datamodels/status_stretch_camera.py:47-82): np.rot90(img, -1) for the d435i cameras, np.rot90(img, 1)
+        for the nav camera (outputs become [n,W,H(,3)]) and RGB->BGR -- fused into the render kernel."""
         self._require()
         import torch
         cams = cameras if cameras is not None else self.cameras_to_use
@@ -224,12 +228,16 @@ class StretchMujocoSimulator:
                 raise ValueError(f"Tried to get {cam} imagery, but it is not available")
             W, H = width or cs.width, height or cs.height
             dev = self.batch.qpos.device
+            rot = 0
+            if auto_rotate:
+                rot = -1 if "d435i" in cs.name_in_mjcf else (1 if "nav" in cs.name_in_mjcf else 0)
+            oh, ow = (W, H) if rot else (H, W)
             if cs.is_depth:
-                img = torch.empty(n, H, W, dtype=torch.float32, device=dev)
-                self.batch.render(cid, W, H, cs.fovy, None, img, cs.depth_limit, env_begin, n)
+                img = torch.empty(n, oh, ow, dtype=torch.float32, device=dev)
+                self.batch.render(cid, W, H, cs.fovy, None, img, cs.depth_limit, env_begin, n, rot90=rot)
             else:
-                img = torch.empty(n, H, W, 3, dtype=torch.uint8, device=dev)
-                self.batch.render(cid, W, H, cs.fovy, img, None, 0.0, env_begin, n)
+                img = torch.empty(n, oh, ow, 3, dtype=torch.uint8, device=dev)
+                self.batch.render(cid, W, H, cs.fovy, img, None, 0.0, env_begin, n, rot90=rot, bgr=auto_correct_rgb)
             out[cam] = img
         out["cam_d405_K"] = enums.compute_K(58, 1280, 720)    # camera_manager.py:168-183
         out["cam_d435i_K"] = enums.compute_K(42, 1920, 1080)

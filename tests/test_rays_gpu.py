@@ -232,3 +232,22 @@ def test_kitchen_proxy_physics_lidar_and_cameras(kitchen):
     B.step(300); torch.cuda.synchronize()
     assert torch.isfinite(B.qpos).all() and int((B.env_flags & 1).max()) == 0
     assert float(B.qpos[0, 29]) > 0.9
+
+
+def test_render_post_processing_matches_numpy(scene, posed):
+    """rot90 / BGR fused into the render epilogue == numpy on the plain render
+    (what StatusStretchCameras.get_camera_data does on the reference's client, status_stretch_camera.py:47-82)."""
+    from stretch_mujoco_b200 import engine
+    B, dm = posed, scene["dm"]
+    W, H = 106, 60
+    for cam_name, k in (("d435i_camera_rgb", -1), ("nav_camera_rgb", 1), ("d405_rgb", 0)):
+        cam = dm.name2id(engine.OBJ_CAMERA, cam_name)
+        rgb0 = torch.zeros(4, H, W, 3, dtype=torch.uint8, device="cuda"); d0 = torch.zeros(4, H, W, device="cuda")
+        B.render(cam, W, H, 60.0, rgb0, d0, 5.0)
+        oh, ow = (W, H) if k else (H, W)
+        rgb1 = torch.zeros(4, oh, ow, 3, dtype=torch.uint8, device="cuda"); d1 = torch.zeros(4, oh, ow, device="cuda")
+        B.render(cam, W, H, 60.0, rgb1, d1, 5.0, rot90=k, bgr=True)
+        torch.cuda.synchronize()
+        a, b = rgb0.cpu().numpy(), d0.cpu().numpy()
+        assert np.array_equal(rgb1.cpu().numpy(), np.rot90(a, k, axes=(1, 2))[..., ::-1])
+        assert np.array_equal(d1.cpu().numpy(), np.rot90(b, k, axes=(1, 2)))
