@@ -1549,12 +1549,10 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     q1 = warp_sum(q1); q2 = warp_sum(q2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
-    float p1, p2, a = 0, lo = 0, hi = -1, dlo, dhi = 0;
-    { float4 e = eval_constraints<false>(R, 0.f, lane); p1 = e.y + q1; p2 = e.z + q2; }
-    if (!(p1 < 0) || !(p2 > 0)) { done = true; continue; }
-    float d0 = p1;
-    dlo = p1;
-    a = -p1 / p2;
+    // p'(0) = grad . search = gs and p''(0) = search^T H search = -gs, because search solves H search = -grad
+    // with the Hessian of the CURRENT constraint states: the probe at 0 is free and the first trial step is 1
+    float p1 = gs, p2 = -gs, a = 1.f, lo = 0, hi = -1, dlo = gs, dhi = 0;
+    const float d0 = gs;
     for (int it = 0; it < m.ls_iterations; it++) {
       { float4 e = eval_constraints<false>(R, a, lane); p1 = e.y + q1 + a * q2; p2 = e.z + q2; }
       if (fabsf(p1) < gtol || fabsf(p1) < 1e-6f * fabsf(d0)) break;
