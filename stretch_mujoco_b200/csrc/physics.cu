@@ -24,7 +24,20 @@
 #define MINIMP 0.0001f
 #define MAXIMP 0.9999f
 
-extern __shared__ __align__(16) float smem[];  // [model pack | env slice 0 | env slice 1 | ...]
+extern __shared__ __align__(16) float smem[];
+// Optional cycle accounting per stage (make PROFILE=1; tests/prof_solver.py reads it through ss_debug_prof)
+#ifdef SS_PROFILE
+__device__ unsigned long long g_prof[32];
+#define PROF_BEGIN() long long tprof = clock64()
+#define PROF(k) do { long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[k], (unsigned long long)(t_ - tprof)); tprof = t_; } while (0)
+#define PROF_ADD(k, t0) do { if (lane == 0) atomicAdd(&g_prof[k], (unsigned long long)(clock64() - (t0))); } while (0)
+#define PROF_NOW() clock64()
+#else
+#define PROF_BEGIN() do { } while (0)
+#define PROF(k) do { } while (0)
+#define PROF_ADD(k, t0) do { } while (0)
+#define PROF_NOW() 0
+#endif  // [model pack | env slice 0 | env slice 1 | ...]
 #define PKF(name) (smem + m.pk.name)
 #define PKI(name) (reinterpret_cast<const int*>(smem) + m.pk.name)
 
@@ -526,7 +539,9 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
     }
   }
   }
+  PROF_BEGIN();
   bool any = sync ? group_sync_or(sync, alive) : alive;
+  PROF(work ? 5 : 6);
   if (work) chol_solve_rows<NT>(h, H, nv, ld, xs, lane);
   return any;
 }
@@ -1159,6 +1174,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
     }
     unsigned mask = __ballot_sync(FULL, pass);
     nnarrow += __popc(mask);
+    long long tn0 = PROF_NOW(); (void)tn0;
     while (mask) {
       int bit = __ffs(mask) - 1;
       mask &= mask - 1;
@@ -1192,6 +1208,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       }
       __syncwarp();
     }
+    PROF_ADD(30, tn0);
   }
   __syncwarp();
 }
@@ -1517,6 +1534,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   }
   }
   int iter = 0;
+  PROF_BEGIN();
   while (true) {
     if (!sync && done) break;
     if (!done) {
@@ -1528,6 +1546,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       if (iter >= m.iterations) done = true;
       else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
     }
+    PROF(done ? 7 : 0);
     if (nv <= 32) {
       // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
       // every warp whether any warp of the CTA is still iterating
@@ -1536,6 +1555,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       if (sync && !group_sync_or(sync, !done)) break;
       if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
     }
+    PROF(done ? 7 : 1);
     if (done) continue;
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
@@ -1547,6 +1567,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     float q1 = 0, q2 = 0;
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { q1 += search[i] * (Ma[i] - qs[i]); q2 += search[i] * mv[i]; }
     q1 = warp_sum(q1); q2 = warp_sum(q2);
+    PROF(2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
     // p'(0) = grad . search = gs and p''(0) = search^T H search = -gs, because search solves H search = -grad
@@ -1569,6 +1590,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       }
       a = an;
     }
+    PROF(3);
     if (!(a > 0)) { done = true; continue; }
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
@@ -1581,6 +1603,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       cost += warp_sum(gsum);
     }
     iter++;
+    PROF(4);
     // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
     if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
       mul_JT(R, qfc, force, lane);
@@ -1772,6 +1795,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
     if (slot - (warp - w0) >= a.nenv) break;
     bool active = slot < a.nenv;
     int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
+    PROF_BEGIN();
     int cost = 0;
     if (a.sync_level & 96) {   // debug: scrub the env slice (32: zeros, 64: NaNs) to expose reads of stale shared memory
       float fill = (a.sync_level & 64) ? __int_as_float(0x7fc00000) : 0.f;
@@ -1797,17 +1821,26 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
           flags |= 1;
         }
         STAGE_SYNC(1);
+        PROF(16);
         if (active) kinematics(m, S, lane);
+        PROF(17);
         STAGE_SYNC(2);
         if (active) crb_mass_matrix(m, S, lane);
+        PROF(18);
         STAGE_SYNC(1);
+        PROF(19);
         if (active) collision(m, S, fi.ncon, fi.nnarrow, flags, hs, lane);
+        PROF(20);
         STAGE_SYNC(1);
+        PROF(21);
         if (active) velocity_stage(m, S, lane);
+        PROF(22);
         STAGE_SYNC(2);
         if (active) smooth_forces(m, S, lane);
+        PROF(23);
         STAGE_SYNC(2);
         if (active) make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
+        PROF(24);
         STAGE_SYNC(1);
         // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
         {
@@ -1815,7 +1848,9 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (active) copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
         if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, active, ssync);
         else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+        PROF(25);
         fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
+        PROF(26);
         cost = a.cost_w * fi.iter + fi.nnarrow;   // last step's cost: the predictor for the next launch's schedule
         if (active) _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
         __syncwarp();
@@ -1855,7 +1890,9 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
         if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
         __syncwarp();
       }
+      PROF(27);
       if (!a.forward_only) { integrate(m, S, lane, active, (a.sync_level & 8) ? bar : 0); time += m.timestep; }
+      PROF(28);
     }
     if (!a.forward_only && active) {
       _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
@@ -1864,6 +1901,20 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const Dev
     }
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
     if (lane == 0 && active && !a.forward_only) a.cost[env] = cost;
+    PROF(29);
     __syncwarp();
   }
+}
+
+// cycle counters of the profiling build (32 x u64); returns -1 when the library was built without PROFILE=1
+extern "C" int ss_debug_prof(unsigned long long* out32, int reset) {
+#ifdef SS_PROFILE
+  unsigned long long z[32] = {0};
+  if (out32) cudaMemcpyFromSymbol(out32, g_prof, sizeof(z));
+  if (reset) cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  return 0;
+#else
+  (void)out32; (void)reset;
+  return -1;
+#endif
 }
