@@ -1169,6 +1169,28 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
             }
             if (fabsf(dot3(t, a1)) > r1 || fabsf(dot3(t, a2)) > r2) pass = false;
           }
+          if (pass) {
+            // the nine edge-edge axes L = a1_i x a2_j of the separating-axis test (in box 1's frame:
+            // C = R1^T R2, T = R1^T t); the margin inflates the projection by margin * |L| <= margin
+            float C[9], AC[9], T[3];
+            for (int i = 0; i < 3; i++) {
+              T[i] = R1[i] * t[0] + R1[3 + i] * t[1] + R1[6 + i] * t[2];
+              for (int j = 0; j < 3; j++) {
+                C[3 * i + j] = R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j];
+                AC[3 * i + j] = fabsf(C[3 * i + j]) + 1e-6f;
+              }
+            }
+            const float *h1 = ab1 + 3, *h2 = ab2 + 3;
+            for (int i = 0; i < 3 && pass; i++) {
+              int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+              for (int j = 0; j < 3; j++) {
+                int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                float ra = h1[i1] * AC[3 * i2 + j] + h1[i2] * AC[3 * i1 + j];
+                float rb = h2[j1] * AC[3 * i + j2] + h2[j2] * AC[3 * i + j1];
+                if (fabsf(T[i2] * C[3 * i1 + j] - T[i1] * C[3 * i2 + j]) > ra + rb + margin) pass = false;
+              }
+            }
+          }
         }
       }
     }
