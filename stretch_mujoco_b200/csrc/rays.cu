@@ -517,32 +517,93 @@ __device__ __forceinline__ void stage_geoms(const RayModel& r, const float* xf, 
 #define RAY_SMEM_BYTES(r) ((size_t)(r).nraygeom * (16 + 12) * sizeof(float))
 
 // ----------------------------------------------------------------------------- lidar
-__global__ void lidar_kernel(RayModel r, int nenv, int nsensordata, const float* __restrict__ xpos, const float* __restrict__ xquat,
-                             const float* __restrict__ xf_all, float* __restrict__ out, float* __restrict__ sensordata) {
+// One block per env, one warp per bundle of 32 consecutive rangefinders.  The bundle's rays are enclosed in a
+// cone (apex = the first ray's origin widened by the largest origin offset, axis = mean direction); geoms whose
+// bounding sphere misses the cone are dropped once per bundle (one geom per lane, ballot compaction into the
+// warp's list, geom-id order kept), then every lane traces its ray over the survivors.
+#define LIDAR_WARPS 4
+__global__ void __launch_bounds__(32 * LIDAR_WARPS) lidar_kernel(RayModel r, int nenv, int nsensordata, const float* __restrict__ xpos,
+                                                                const float* __restrict__ xquat, const float* __restrict__ xf_all,
+                                                                float* __restrict__ out, float* __restrict__ sensordata) {
   extern __shared__ float4 sm4[];
   float4* srec = sm4;
   float* sxf = reinterpret_cast<float*>(sm4 + 4 * r.nraygeom);
-  int e = blockIdx.x;
+  int* wlist = reinterpret_cast<int*>(sxf + 12 * r.nraygeom) + (threadIdx.x >> 5) * r.nraygeom;   // [LIDAR_WARPS][nraygeom]
+  const int e = blockIdx.x, lane = threadIdx.x & 31;
   stage_geoms(r, xf_all + (size_t)e * r.nraygeom * 12, srec, sxf, threadIdx.x, blockDim.x);
   __syncthreads();
-  for (int s = threadIdx.x; s < r.nrange; s += blockDim.x) {
-    int site = r.range_site[s], b = r.site_bodyid[site];
-    const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
-    float Rb[9], q[4], bqq[4] = {bq[0], bq[1], bq[2], bq[3]}, R[9];
-    float sq[4] = {r.site_quat[4 * site], r.site_quat[4 * site + 1], r.site_quat[4 * site + 2], r.site_quat[4 * site + 3]};
-    float sp[3] = {r.site_pos[3 * site], r.site_pos[3 * site + 1], r.site_pos[3 * site + 2]};
-    q2m(Rb, bqq);
-    float p[3] = {bp[0] + Rb[0] * sp[0] + Rb[1] * sp[1] + Rb[2] * sp[2], bp[1] + Rb[3] * sp[0] + Rb[4] * sp[1] + Rb[5] * sp[2],
-                  bp[2] + Rb[6] * sp[0] + Rb[7] * sp[1] + Rb[8] * sp[2]};
-    qmul(q, bqq, sq);
-    q2m(R, q);
-    float dir[3] = {R[2], R[5], R[8]};
-    Hit h = trace_scene<true>(r, sxf, srec, r.nraygeom, p, dir, 0.f, 0, b);
-    float dist = h.t;
-    float cut = r.range_cutoff[s];
-    if (dist >= 0 && cut > 0 && dist > cut) dist = cut;
-    if (out) out[(size_t)e * r.nrange + s] = dist;
-    if (sensordata) sensordata[(size_t)e * nsensordata + r.range_adr[s]] = dist;
+  for (int base = (threadIdx.x >> 5) * 32; base < r.nrange; base += blockDim.x) {
+    const int s = base + lane;
+    const bool live = s < r.nrange;
+    float p[3] = {0, 0, 0}, dir[3] = {0, 0, 0};
+    int b = -1;
+    if (live) {
+      int site = r.range_site[s];
+      b = r.site_bodyid[site];
+      const float *bp = xpos + ((size_t)e * r.nbody + b) * 3, *bq = xquat + ((size_t)e * r.nbody + b) * 4;
+      float Rb[9], q[4], bqq[4] = {bq[0], bq[1], bq[2], bq[3]}, R[9];
+      float sq[4] = {r.site_quat[4 * site], r.site_quat[4 * site + 1], r.site_quat[4 * site + 2], r.site_quat[4 * site + 3]};
+      float sp[3] = {r.site_pos[3 * site], r.site_pos[3 * site + 1], r.site_pos[3 * site + 2]};
+      q2m(Rb, bqq);
+      p[0] = bp[0] + Rb[0] * sp[0] + Rb[1] * sp[1] + Rb[2] * sp[2];
+      p[1] = bp[1] + Rb[3] * sp[0] + Rb[4] * sp[1] + Rb[5] * sp[2];
+      p[2] = bp[2] + Rb[6] * sp[0] + Rb[7] * sp[1] + Rb[8] * sp[2];
+      qmul(q, bqq, sq);
+      q2m(R, q);
+      dir[0] = R[2]; dir[1] = R[5]; dir[2] = R[8];
+    }
+    // bundle cone: apex a (lane 0's origin), axis = normalised sum of the unit directions, cos of the half angle,
+    // and the largest distance of an origin from the apex (0 for the Stretch lidar: all sites coincide)
+    float ax[3], a0[3], cosa, spread;
+    {
+      float sx = dir[0], sy = dir[1], sz = dir[2];
+      for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o); }
+      float n = rsqrtf(fmaxf(sx * sx + sy * sy + sz * sz, 1e-20f));
+      ax[0] = sx * n; ax[1] = sy * n; ax[2] = sz * n;
+      for (int k = 0; k < 3; k++) a0[k] = __shfl_sync(0xffffffffu, p[k], 0);
+      float c = live ? dir[0] * ax[0] + dir[1] * ax[1] + dir[2] * ax[2] : 1.f;
+      float d2 = live ? (p[0] - a0[0]) * (p[0] - a0[0]) + (p[1] - a0[1]) * (p[1] - a0[1]) + (p[2] - a0[2]) * (p[2] - a0[2]) : 0.f;
+      for (int o = 16; o > 0; o >>= 1) { c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o)); d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o)); }
+      cosa = c; spread = sqrtf(d2);
+    }
+    const float sina = sqrtf(fmaxf(1.f - cosa * cosa, 0.f));
+    const int bx = __shfl_sync(0xffffffffu, b, 0);
+    const bool same_body = __all_sync(0xffffffffu, !live || b == bx);
+    int nl = 0;
+    for (int kb = 0; kb < r.nraygeom; kb += 32) {
+      int k = kb + lane;
+      bool keep = false;
+      if (k < r.nraygeom) {
+        const float4* rec = srec + 4 * k;
+        keep = true;
+        if (same_body && REC_BODY(rec) == bx) keep = false;            // the sensor's own body (mj_ray bodyexclude)
+        else if (cosa > 0.f && REC_TYPE(rec) != GEOM_PLANE) {           // cone test only for bundles narrower than 180 degrees
+          const float* T = sxf + 12 * k;
+          float d[3] = {T[0] - a0[0], T[1] - a0[1], T[2] - a0[2]};
+          float rb = rec[1].x + spread, dist2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+          if (dist2 > rb * rb) {
+            float dist = sqrtf(dist2), sb = rb / dist, cb = sqrtf(1.f - sb * sb);
+            float cang = (d[0] * ax[0] + d[1] * ax[1] + d[2] * ax[2]) / dist;   // cos of the angle centre-axis
+            keep = cang >= cosa * cb - sina * sb - 1e-5f;                        // angle <= alpha + beta
+          }
+        }
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) wlist[nl + __popc(mask & ((1u << lane) - 1))] = k;
+      nl += __popc(mask);
+    }
+    __syncwarp();
+    if (live) {
+      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      const float vv = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+      for (int i = 0; i < nl; i++) trace_one<true>(r, sxf, srec, wlist[i], p, dir, vv, 0.f, 0, b, h);
+      float dist = h.t;
+      float cut = r.range_cutoff[s];
+      if (dist >= 0 && cut > 0 && dist > cut) dist = cut;
+      if (out) out[(size_t)e * r.nrange + s] = dist;
+      if (sensordata) sensordata[(size_t)e * nsensordata + r.range_adr[s]] = dist;
+    }
+    __syncwarp();
   }
 }
 
@@ -765,9 +826,9 @@ extern "C" int ss_batch_lidar(ss_batch* B, float* out_dev, ss_stream s) {
   if (prepare(B, st) != 0) return -1;
   const RayModel& r = B->model->rm;
   if (r.nrange == 0) return ss_fail("model has no rangefinder sensors");
-  size_t smem = RAY_SMEM_BYTES(r);
+  size_t smem = RAY_SMEM_BYTES(r) + (size_t)LIDAR_WARPS * r.nraygeom * sizeof(int);
   cudaFuncSetAttribute(lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  lidar_kernel<<<B->nenv, 128, smem, st>>>(r, B->nenv, B->dm.nsensordata, B->bufs.xpos, B->bufs.xquat, B->ray_xf, out_dev,
+  lidar_kernel<<<B->nenv, 32 * LIDAR_WARPS, smem, st>>>(r, B->nenv, B->dm.nsensordata, B->bufs.xpos, B->bufs.xquat, B->ray_xf, out_dev,
                                            out_dev ? nullptr : B->bufs.sensordata);
   B->launches++;
   CUDA_OK(cudaGetLastError());
