@@ -414,6 +414,11 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   B->steps_per_launch = 1;   // measured (1 set): 50 -> 56.0, 10 -> 54.7, 5 -> 53.9, 2 -> 53.2, 1 -> 53.6 ms per 50 steps x 4096 envs; (2 sets): 2 -> 48.9, 1 -> 47.9
   if (const char* e = getenv("SS_CHUNK")) B->steps_per_launch = std::max(1, atoi(e));
   B->nosort = getenv("SS_NOSORT") != nullptr;
+  // schedule key: bucket = min(255, cost_scale * cost), cost = cost_w x Newton iterations + narrowphase queries
+  // (47.3 ms per 50 steps for 16 / x1 against 47.9 ms for 8 / x4)
+  B->cost_w = 16; B->cost_scale = 1;
+  if (const char* e = getenv("SS_COSTW")) B->cost_w = atoi(e);
+  if (const char* e = getenv("SS_COSTSCALE")) B->cost_scale = atoi(e);
   B->nsets = nenv >= 8 * sms ? 2 : 1;   // measured at 4096 envs: 1 set 53.2 ms, 2 sets 48.9 ms, 4 sets 48.8 ms per 50 steps
   if (const char* e = getenv("SS_SETS")) B->nsets = std::max(1, std::min(SS_MAXSETS, atoi(e)));
   if (B->nsets > 1) {
@@ -453,8 +458,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   StepArgs a;
   memset(&a, 0, sizeof(a));
   const ss_buffers& f = B->bufs;
-  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level; a.group_warps = B->group_warps; a.cost_w = 16;
-  if (const char* e = getenv("SS_COSTW")) a.cost_w = atoi(e);
+  a.nenv = B->nenv; a.nsteps = nsteps; a.forward_only = forward_only; a.sync_level = B->sync_level; a.group_warps = B->group_warps; a.cost_w = B->cost_w;
   a.qpos = f.qpos; a.qvel = f.qvel; a.warm = f.qacc_warmstart; a.time = f.time; a.ctrl = f.ctrl;
   a.xpos = f.xpos; a.xquat = f.xquat; a.act_length = f.act_length; a.act_velocity = f.act_velocity;
   a.sensordata = f.sensordata; a.qacc = f.qacc; a.ncon = f.ncon; a.contact_geom = f.contact_geom;
@@ -471,8 +475,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   // The env batch is cut into `nsets` contiguous sets whose launch chains run on library-owned side
   // streams, forked from and joined back into the caller's stream by events: the persistent CTAs of one
   // set drain while the next set's CTAs take over the freed SMs, which hides the tail of every launch.
-  int cost_scale = 1;   // bucket = min(255, cost); cost = 16 x Newton iterations + narrowphase queries (47.3 vs 47.9 ms for 8 / x4)
-  if (const char* e = getenv("SS_COSTSCALE")) cost_scale = atoi(e);
+  const int cost_scale = B->cost_scale;
   cudaStream_t user = (cudaStream_t)stream;
   int chunk = forward_only ? 1 : B->steps_per_launch;
   int nsets = (forward_only || nsteps <= chunk) ? 1 : B->nsets;

@@ -35,6 +35,7 @@ struct ss_batch {
   long launches;
   int steps_per_launch = 1;   // long rollouts are cut into launches of this many steps, re-sorted in between
   bool nosort = false;
+  int cost_w = 16, cost_scale = 1;
   int nsets = 1;               // env sets with their own launch chains on side streams (tail overlap)
   cudaStream_t side[SS_MAXSETS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[SS_MAXSETS] = {};
