@@ -148,7 +148,7 @@ static double ray_mesh(const om_model* m, const struct om_rayaccel* A, int mid, 
     if (n->left < 0) {
       for (int i = n->first; i < n->first + n->count; i++) {
         const int* f = F + 3 * B->tri[i];
-        double tn[3];
+        double tn[3] = {0, 0, 0};
         double x = ray_tri(V + 3 * f[0], V + 3 * f[1], V + 3 * f[2], o, d, tn);
         if (x >= tmin && (best < 0 || x < best)) { best = x; if (nrm) v3copy(nrm, tn); }
       }
