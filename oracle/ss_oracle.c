@@ -88,6 +88,8 @@ om_model* om_model_load(const void* buf, size_t nbytes) {
   D(pair_margin, "pair_margin"); D(pair_gap, "pair_gap");
   I(mesh_hulladr, "mesh_hulladr"); I(mesh_hullnum, "mesh_hullnum"); D(hull_vert, "hull_vert");
   D(key_qpos, "key_qpos"); D(key_ctrl, "key_ctrl");
+  if (ss_blob_find(&b, "hull_edgeadr")) { I(hull_edgeadr, "hull_edgeadr"); I(hull_edge, "hull_edge"); }
+  m->multiccd = ss_blob_find(&b, "opt_multiccd") ? ss_blob_i32(&b, "opt_multiccd")[0] : 0;
   /* ray geometry (optional) */
   if (ss_blob_find(&b, "rmesh_vertadr")) {
     m->has_ray = 1;

@@ -5,9 +5,10 @@
  * sphere test and the narrowphase.  Plane-vs-primitive routines restate MuJoCo's analytic
  * functions [upstream mjc_PlaneSphere/PlaneCylinder/PlaneBox]; every other convex pair runs
  * Minkowski Portal Refinement, the algorithm of libccd's ccdMPRPenetration that MuJoCo 3.2.6
- * calls for convex pairs [upstream mjc_Convex].  DEVIATIONS (documented in DESIGN.md): the
- * `multiccd` extra contacts and the plane-mesh extra contacts are not generated; box-box and
- * sphere-box go through MPR instead of their analytic routines.
+ * calls for convex pairs [upstream mjc_Convex], including the `multiccd` perturbation contacts the
+ * reference enables (`stretch_mujoco/models/stretch.xml:8`).  Plane-mesh adds up to three hull
+ * neighbours of the support vertex [upstream mjc_PlaneConvex]; box-box and sphere-box are analytic
+ * (own SAT + face clipping restatement; MuJoCo's mjc_BoxBox point ordering is not reproduced).
  */
 #include "ss_oracle.h"
 #include "ss_oracle_internal.h"
@@ -43,10 +44,12 @@ static om_contact* add_contact(const om_model* m, om_data* d, int pair, double d
 
 typedef struct {
   int type; const double *pos, *mat, *size; const double* verts; int nvert;
+  const int *edgeadr, *edge;   /* hull adjacency (NULL when the blob carries none) */
 } cvx;
 
-static void support(const cvx* g, const double* dir, double* out) {
+static int support(const cvx* g, const double* dir, double* out) {
   double l[3], r[3] = {0, 0, 0};
+  int index = -1;
   multmatvec3(l, g->mat, dir);
   switch (g->type) {
     case GEOM_SPHERE: {
@@ -68,11 +71,13 @@ static void support(const cvx* g, const double* dir, double* out) {
         if (s > best) { best = s; bi = i; }
       }
       v3copy(r, g->verts + 3 * bi);
+      index = bi;
     } break;
     default: break;
   }
   mulmatvec3(out, g->mat, r);
   v3addto(out, g->pos);
+  return index;
 }
 
 typedef struct { double v[3], v1[3], v2[3]; } spt;
@@ -231,10 +236,11 @@ static int mpr_penetration(const cvx* A, const cvx* B, double* depth, double* di
 
 static void cvx_of(const om_model* m, const om_data* d, int g, cvx* c) {
   c->type = m->geom_type[g]; c->pos = d->geom_xpos + 3 * g; c->mat = d->geom_xmat + 9 * g;
-  c->size = m->geom_size + 3 * g; c->verts = NULL; c->nvert = 0;
+  c->size = m->geom_size + 3 * g; c->verts = NULL; c->nvert = 0; c->edgeadr = NULL; c->edge = NULL;
   if (c->type == GEOM_MESH) {
     int mid = m->geom_dataid[g];
     c->verts = m->hull_vert + 3 * m->mesh_hulladr[mid]; c->nvert = m->mesh_hullnum[mid];
+    if (m->hull_edgeadr) { c->edgeadr = m->hull_edgeadr + m->mesh_hulladr[mid]; c->edge = m->hull_edge; }
   }
 }
 
@@ -304,28 +310,236 @@ static void plane_box(const om_model* m, om_data* d, int pair, int g1, int g2, d
   }
 }
 
+/* [upstream mjc_PlaneConvex] support vertex, then up to three of its hull neighbours within the margin */
 static void plane_mesh(const om_model* m, om_data* d, int pair, int g1, int g2, double margin) {
   const double *pp = d->geom_xpos + 3 * g1, *pm = d->geom_xmat + 9 * g1;
   double n[3] = {pm[2], pm[5], pm[8]}, nd[3] = {-pm[2], -pm[5], -pm[8]}, s[3], dif[3], pos[3];
   cvx g;
   cvx_of(m, d, g2, &g);
-  support(&g, nd, s);
+  int v0 = support(&g, nd, s);
   v3sub(dif, s, pp);
   double dist = v3dot(dif, n);
   if (dist > margin) return;
   v3addscl(pos, s, n, -0.5 * dist);
   add_contact(m, d, pair, dist, pos, n);
+  if (!g.edgeadr || v0 < 0) return;
+  int cnt = 1;
+  for (int e = g.edgeadr[v0]; e < g.edgeadr[v0 + 1] && cnt < 4; e++) {
+    double w[3];
+    mulmatvec3(w, g.mat, g.verts + 3 * g.edge[e]);
+    v3addto(w, g.pos);
+    v3sub(dif, w, pp);
+    dist = v3dot(dif, n);
+    if (dist > margin) continue;
+    v3addscl(pos, w, n, -0.5 * dist);
+    add_contact(m, d, pair, dist, pos, n);
+    cnt++;
+  }
 }
 
+/* one MPR query -> contact candidate [upstream mjc_MPRIteration] */
+static int mpr_contact(const cvx* A, const cvx* B, double margin, double* dist, double* dir, double* pos) {
+  double depth;
+  if (!mpr_penetration(A, B, &depth, dir, pos)) return 0;
+  if (v3dot(dir, dir) < 0.5) return 0; /* touching contact without a direction */
+  *dist = margin - depth;
+  return 1;
+}
+
+/* rotate the frame (mat, pos) about `origin` by rot [upstream mju_rotateFrame in engine_collision_convex.c] */
+static void rotate_frame(const double* origin, const double* rot, double* mat, double* pos) {
+  double t[9], rel[3], v[3];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) t[3 * r + c] = rot[3 * r] * mat[c] + rot[3 * r + 1] * mat[3 + c] + rot[3 * r + 2] * mat[6 + c];
+  memcpy(mat, t, sizeof(t));
+  v3sub(rel, pos, origin);
+  mulmatvec3(v, rot, rel);
+  v3add(pos, origin, v);
+}
+
+/* [upstream mjc_Convex] MPR contact, then -- with the multiccd flag the reference sets
+ * (stretch_mujoco/models/stretch.xml:8) -- four more queries with both geoms counter-rotated by
+ * +-1e-3 rad about the two tangent axes of the first contact; a new contact is kept when its position
+ * is farther than 1e-3 * min(rbound) from every contact found so far. */
 static void convex_convex(const om_model* m, om_data* d, int pair, int g1, int g2, double margin) {
   cvx A, B;
-  double depth, dir[3], pos[3];
-  (void)margin;
+  double dist, dir[3], pos[3];
   cvx_of(m, d, g1, &A); cvx_of(m, d, g2, &B);
-  if (!mpr_penetration(&A, &B, &depth, dir, pos)) return;
-  if (v3dot(dir, dir) < 0.5) return; /* touching contact without a direction */
-  /* dir = direction along which B must move to leave A, i.e. the geom1 -> geom2 contact normal */
-  add_contact(m, d, pair, -depth, pos, dir);
+  if (!mpr_contact(&A, &B, margin, &dist, dir, pos)) return;
+  if (!add_contact(m, d, pair, dist, pos, dir)) return;
+  int t1 = A.type, t2 = B.type;
+  if (!m->multiccd || t1 == GEOM_SPHERE || t1 == GEOM_ELLIPSOID || t2 == GEOM_SPHERE || t2 == GEOM_ELLIPSOID) return;
+  double found[5][3], frame[9];
+  int nfound = 1;
+  v3copy(found[0], pos);
+  v3copy(frame, dir); make_frame(frame);
+  double tol = 1e-3 * (m->geom_rbound[g1] < m->geom_rbound[g2] ? m->geom_rbound[g1] : m->geom_rbound[g2]);
+  for (int axis_id = 0; axis_id < 2; axis_id++)
+    for (int angle_id = 0; angle_id < 2; angle_id++) {
+      const double* axis = frame + 3 + 3 * axis_id;
+      double angle = angle_id ? 1e-3 : -1e-3, q[4], rot[9], irot[9];
+      axisangle2quat(q, axis, angle);
+      quat2mat(rot, q);
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) irot[3 * r + c] = rot[3 * c + r];
+      double pA[3], mA[9], pB[3], mB[9];
+      v3copy(pA, A.pos); memcpy(mA, A.mat, 72); v3copy(pB, B.pos); memcpy(mB, B.mat, 72);
+      rotate_frame(found[0], rot, mA, pA);
+      rotate_frame(found[0], irot, mB, pB);
+      cvx A2 = A, B2 = B;
+      A2.pos = pA; A2.mat = mA; B2.pos = pB; B2.mat = mB;
+      double dist2, dir2[3], pos2[3];
+      if (!mpr_contact(&A2, &B2, margin, &dist2, dir2, pos2)) continue;
+      int distinct = 1;
+      for (int k = 0; k < nfound; k++) {
+        double df[3]; v3sub(df, found[k], pos2);
+        if (v3norm(df) < tol) distinct = 0;
+      }
+      if (!distinct) continue;
+      if (!add_contact(m, d, pair, dist2, pos2, dir2)) return;
+      v3copy(found[nfound++], pos2);
+    }
+}
+
+/* sphere-box [upstream mjc_SphereBox]: closest point of the box to the sphere centre */
+static void sphere_box(const om_model* m, om_data* d, int pair, int g1, int g2, double margin) {
+  const double *ps = d->geom_xpos + 3 * g1, *pb = d->geom_xpos + 3 * g2, *Rb = d->geom_xmat + 9 * g2, *sz = m->geom_size + 3 * g2;
+  double r = m->geom_size[3 * g1], dif[3], c[3], q[3], dl[3];
+  v3sub(dif, ps, pb);
+  multmatvec3(c, Rb, dif);
+  int inside = 1;
+  for (int k = 0; k < 3; k++) {
+    q[k] = c[k] < -sz[k] ? -sz[k] : (c[k] > sz[k] ? sz[k] : c[k]);
+    if (q[k] != c[k]) inside = 0;
+  }
+  double nl[3] = {0, 0, 0}, dist;   /* nl: box -> sphere, box frame */
+  if (!inside) {
+    v3sub(dl, c, q);
+    double len = v3norm(dl);
+    dist = len - r;
+    if (dist > margin) return;
+    v3scl(nl, dl, 1.0 / len);
+  } else {
+    int best = 0; double bd = 1e300;
+    for (int k = 0; k < 3; k++) { double t = sz[k] - fabs(c[k]); if (t < bd) { bd = t; best = k; } }
+    nl[best] = c[best] >= 0 ? 1 : -1;
+    q[best] = nl[best] * sz[best];
+    dist = -bd - r;
+  }
+  double nw[3], qw[3], n[3], pos[3];
+  mulmatvec3(nw, Rb, nl); mulmatvec3(qw, Rb, q); v3addto(qw, pb);
+  v3scl(n, nw, -1);   /* geom1 (sphere) -> geom2 (box) */
+  v3addscl(pos, qw, nw, 0.5 * dist);
+  add_contact(m, d, pair, dist, pos, n);
+}
+
+/* clip a convex polygon (n <= 8 vertices, 2-D coordinates) against u <= lim (sign=+1) or u >= -lim (sign=-1) */
+static int clip_axis(double (*poly)[2], int n, int axis, double sign, double lim) {
+  double out[16][2];
+  int no = 0;
+  for (int i = 0; i < n; i++) {
+    const double *a = poly[i], *b = poly[(i + 1) % n];
+    double da = sign * a[axis] - lim, db = sign * b[axis] - lim;
+    if (da <= 0) { out[no][0] = a[0]; out[no][1] = a[1]; no++; }
+    if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+      double t = da / (da - db);
+      out[no][0] = a[0] + t * (b[0] - a[0]); out[no][1] = a[1] + t * (b[1] - a[1]); no++;
+    }
+  }
+  if (no > 8) no = 8;
+  memcpy(poly, out, sizeof(double) * 2 * no);
+  return no;
+}
+
+/* box-box [upstream mjc_BoxBox]: separating-axis test over the 15 axes, then either the incident face
+ * clipped against the reference face (up to 8 points) or one edge-edge point.  Restated as the
+ * textbook algorithm; MuJoCo's own routine may order / merge the points differently. */
+static void box_box(const om_model* m, om_data* d, int pair, int g1, int g2, double margin) {
+  const double *p1 = d->geom_xpos + 3 * g1, *R1 = d->geom_xmat + 9 * g1, *s1 = m->geom_size + 3 * g1;
+  const double *p2 = d->geom_xpos + 3 * g2, *R2 = d->geom_xmat + 9 * g2, *s2 = m->geom_size + 3 * g2;
+  double a1[3][3], a2[3][3], pp[3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { a1[i][k] = R1[3 * k + i]; a2[i][k] = R2[3 * k + i]; }
+  v3sub(pp, p2, p1);
+  double bestf = -1e300, beste = -1e300, nf[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
+  int codef = -1, codee = -1;
+  for (int w = 0; w < 2; w++)
+    for (int i = 0; i < 3; i++) {
+      const double* L = w ? a2[i] : a1[i];
+      double t = v3dot(pp, L), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(v3dot(a1[k], L)); rb += s2[k] * fabs(v3dot(a2[k], L)); }
+      double sep = fabs(t) - ra - rb;
+      if (sep > margin) return;
+      if (sep > bestf) { bestf = sep; codef = 3 * w + i; v3scl(nf, L, t >= 0 ? 1 : -1); }
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double L[3];
+      v3cross(L, a1[i], a2[j]);
+      double len = v3norm(L);
+      if (len < 1e-6) continue;
+      v3scl(L, L, 1.0 / len);
+      double t = v3dot(pp, L), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(v3dot(a1[k], L)); rb += s2[k] * fabs(v3dot(a2[k], L)); }
+      double sep = fabs(t) - ra - rb;
+      if (sep > margin) return;
+      if (sep > beste) { beste = sep; codee = 3 * i + j; v3scl(ne, L, t >= 0 ? 1 : -1); }
+    }
+  if (codee >= 0 && beste > bestf + 0.05 * fabs(bestf) + 1e-9) {
+    /* edge-edge: the closest points of the two supporting edges */
+    int i = codee / 3, j = codee % 3;
+    double c1[3], c2[3];
+    v3copy(c1, p1); v3copy(c2, p2);
+    for (int k = 0; k < 3; k++) {
+      if (k != i) v3addscl(c1, c1, a1[k], (v3dot(ne, a1[k]) > 0 ? 1 : -1) * s1[k]);
+      if (k != j) v3addscl(c2, c2, a2[k], (v3dot(ne, a2[k]) > 0 ? -1 : 1) * s2[k]);
+    }
+    double r[3], b = v3dot(a1[i], a2[j]), den = 1 - b * b;
+    v3sub(r, c2, c1);
+    double d1 = v3dot(r, a1[i]), d2 = v3dot(r, a2[j]);
+    double s = den > 1e-12 ? (d1 - b * d2) / den : 0, t = den > 1e-12 ? (b * d1 - d2) / den : 0;
+    double q1[3], q2[3], pos[3];
+    v3addscl(q1, c1, a1[i], s); v3addscl(q2, c2, a2[j], t);
+    for (int k = 0; k < 3; k++) pos[k] = 0.5 * (q1[k] + q2[k]);
+    add_contact(m, d, pair, beste, pos, ne);
+    return;
+  }
+  /* face contact: reference box owns the axis, incident face of the other box is clipped against it */
+  int refis2 = codef >= 3, ax = codef % 3;
+  const double *pr = refis2 ? p2 : p1, *sr = refis2 ? s2 : s1, *pc = refis2 ? p1 : p2, *sc = refis2 ? s1 : s2;
+  double(*ar)[3] = refis2 ? a2 : a1;
+  double(*ac)[3] = refis2 ? a1 : a2;
+  double nr[3];
+  v3scl(nr, nf, refis2 ? -1 : 1);   /* outward normal of the reference face, towards the incident box */
+  int jc = 0; double bd = -1;
+  for (int k = 0; k < 3; k++) { double t = fabs(v3dot(ac[k], nr)); if (t > bd) { bd = t; jc = k; } }
+  double sgn = v3dot(ac[jc], nr) > 0 ? -1 : 1, fc[3];
+  v3addscl(fc, pc, ac[jc], sgn * sc[jc]);
+  int k1 = (jc + 1) % 3, k2 = (jc + 2) % 3, u = (ax + 1) % 3, v = (ax + 2) % 3;
+  double poly[16][2], hgt[4], quad[4][3];
+  for (int c = 0; c < 4; c++) {
+    double e1 = (c == 0 || c == 3) ? -1 : 1, e2 = c < 2 ? -1 : 1;
+    v3addscl(quad[c], fc, ac[k1], e1 * sc[k1]); v3addscl(quad[c], quad[c], ac[k2], e2 * sc[k2]);
+    double rel[3]; v3sub(rel, quad[c], pr);
+    poly[c][0] = v3dot(rel, ar[u]); poly[c][1] = v3dot(rel, ar[v]); hgt[c] = v3dot(rel, nr);
+  }
+  /* height over the reference plane is affine in the 2-D coordinates: h = h0 + gu*x + gv*y (least squares on the quad) */
+  double e1[2] = {poly[1][0] - poly[0][0], poly[1][1] - poly[0][1]}, e2[2] = {poly[3][0] - poly[0][0], poly[3][1] - poly[0][1]};
+  double dh1 = hgt[1] - hgt[0], dh2 = hgt[3] - hgt[0], det = e1[0] * e2[1] - e1[1] * e2[0];
+  if (fabs(det) < 1e-14) return;
+  double gu = (dh1 * e2[1] - dh2 * e1[1]) / det, gv = (e1[0] * dh2 - e2[0] * dh1) / det;
+  double h0 = hgt[0] - gu * poly[0][0] - gv * poly[0][1];
+  int n = 4;
+  n = clip_axis(poly, n, 0, 1, sr[u]);
+  if (n) n = clip_axis(poly, n, 0, -1, sr[u]);
+  if (n) n = clip_axis(poly, n, 1, 1, sr[v]);
+  if (n) n = clip_axis(poly, n, 1, -1, sr[v]);
+  for (int c = 0; c < n; c++) {
+    double h = h0 + gu * poly[c][0] + gv * poly[c][1], dist = h - sr[ax];
+    if (dist > margin) continue;
+    double pos[3];
+    v3copy(pos, pr);
+    v3addscl(pos, pos, ar[u], poly[c][0]); v3addscl(pos, pos, ar[v], poly[c][1]); v3addscl(pos, pos, nr, h - 0.5 * dist);
+    if (!add_contact(m, d, pair, dist, pos, nf)) return;
+  }
 }
 
 void om_collision(const om_model* m, om_data* d) {
@@ -381,6 +595,10 @@ void om_collision(const om_model* m, om_data* d) {
       else if (t2 == GEOM_CYLINDER) plane_cylinder(m, d, p, g1, g2, margin);
       else if (t2 == GEOM_BOX) plane_box(m, d, p, g1, g2, margin);
       else if (t2 == GEOM_MESH) plane_mesh(m, d, p, g1, g2, margin);
+    } else if (t1 == GEOM_BOX && t2 == GEOM_BOX) {
+      box_box(m, d, p, g1, g2, margin);
+    } else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) {
+      sphere_box(m, d, p, g1, g2, margin);
     } else {
       convex_convex(m, d, p, g1, g2, margin);
     }

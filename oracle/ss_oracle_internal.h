@@ -41,6 +41,7 @@ struct om_model {
   int *pair_geom1, *pair_geom2, *pair_condim;
   double *pair_friction, *pair_solref, *pair_solimp, *pair_margin, *pair_gap;
   int *mesh_hulladr, *mesh_hullnum; double* hull_vert;
+  int *hull_edgeadr, *hull_edge, multiccd;   /* hull adjacency (NULL in blobs that predate it), <flag multiccd> */
   double *key_qpos, *key_ctrl;
   /* ray geometry */
   int has_ray, nraygeom, nsky, nlight, headlight_active;

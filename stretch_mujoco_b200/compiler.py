@@ -409,6 +409,25 @@ def compile_scene(sc: Scene, with_render: bool = True, verbose: bool = False) ->
             hull_adr.append(-1); hull_num.append(0)
     A["mesh_hulladr"] = i32(hull_adr); A["mesh_hullnum"] = i32(hull_num)
     A["hull_vert"] = f64(np.concatenate(hull_verts) if hull_verts else np.zeros((0, 3)), (-1, 3))
+    # hull vertex adjacency ("mesh graph"): hull_edge[hull_edgeadr[v] : hull_edgeadr[v + 1]] are the hull-local ids
+    # of the neighbours of hull vertex v (v indexes hull_vert globally).  UPSTREAM-ASSUMPTION (mjCMesh::MakeGraph):
+    # a vertex's neighbours are listed in the order of the qhull facets that contain it, deduplicated; the
+    # plane-mesh collider walks this list to add up to three more contacts (oracle/ss_oracle_collision.c:plane_mesh).
+    edge_adr, edges = [0], []
+    for ma in mesh_list:
+        if ma.hull_verts is None:
+            continue
+        nbr: list[list[int]] = [[] for _ in range(len(ma.hull_verts))]
+        for f in ma.hull_faces:
+            for k in range(3):
+                v = int(f[k])
+                for w in (int(f[(k + 1) % 3]), int(f[(k + 2) % 3])):
+                    if w not in nbr[v]:
+                        nbr[v].append(w)
+        for lst in nbr:
+            edges += lst
+            edge_adr.append(len(edges))
+    A["hull_edgeadr"] = i32(edge_adr); A["hull_edge"] = i32(edges)
     vis = sc.visual
     stat_extent = sc.statistic.get("extent", [None])[0]
     A["vis_headlight"] = f64([vis["headlight"]["ambient"], vis["headlight"]["diffuse"], vis["headlight"]["specular"]], (3, 3))

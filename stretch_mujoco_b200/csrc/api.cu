@@ -307,6 +307,8 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
   m.pair_friction = upload(M, f32(b, "pair_friction")); m.pair_solref = upload(M, f32(b, "pair_solref"));
   m.pair_solimp = upload(M, f32(b, "pair_solimp")); m.pair_margin = upload(M, pmargin); m.pair_gap = upload(M, f32(b, "pair_gap"));
   m.hull_vert = upload(M, hull4);
+  if (ss_blob_find(&b, "hull_edgeadr")) { m.hull_edgeadr = upload(M, i32(b, "hull_edgeadr")); m.hull_edge = upload(M, i32(b, "hull_edge")); }
+  m.multiccd = ss_blob_find(&b, "opt_multiccd") ? ss_blob_i32(&b, "opt_multiccd")[0] : 0;
   m.key_qpos = upload(M, f32(b, "key_qpos")); m.key_ctrl = upload(M, f32(b, "key_ctrl"));
   M->qpos0_dev = upload(M, M->qpos0_host);
   cudaError_t e = cudaGetLastError();

@@ -82,5 +82,7 @@ struct DevModel {
   const int* pair_condim;
   const float *pair_friction, *pair_solref, *pair_solimp, *pair_margin, *pair_gap;
   const float4* hull_vert;
+  const int *hull_edgeadr, *hull_edge;   // hull vertex adjacency (nullptr when the blob carries none)
+  int multiccd;                          // <flag multiccd> (stretch.xml:8)
   const float *key_qpos, *key_ctrl;
 };

@@ -704,6 +704,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
 // ----------------------------------------------------------------------------- S1c: collision
 struct Cvx {
   int type, nvert, mesh, soff;   // soff: float4 index of the staged hull in shared memory, -1 = not staged
+  int hadr;                      // first hull vertex of the mesh in hull_vert / hull_edgeadr
   float pos[3], mat[9], size[3];
   const float4* verts;
 };
@@ -733,8 +734,9 @@ __device__ __forceinline__ int warp_argmax(float best, int bi) {
 }
 
 // support point of one convex geom in world coordinates (mesh hulls: lane-parallel vertex scan)
-__device__ __forceinline__ void support(const Cvx& g, const float* dir, float* out, int lane) {
+__device__ __forceinline__ int support(const Cvx& g, const float* dir, float* out, int lane) {
   float l[3], r[3];
+  int index = -1;
   matT_vec(l, g.mat, dir);
   if (g.type == GEOM_MESH) {
     float best = -CUDART_INF_F; int bi = 0x7fffffff;
@@ -744,11 +746,13 @@ __device__ __forceinline__ void support(const Cvx& g, const float* dir, float* o
       float s = v.x * l[0] + v.y * l[1] + v.z * l[2];
       if (s > best) { best = s; bi = i; }
     }
-    float4 v = g.verts[warp_argmax(best, bi)];
+    index = warp_argmax(best, bi);
+    float4 v = g.verts[index];
     r[0] = v.x; r[1] = v.y; r[2] = v.z;
   } else support_prim(g, l, r);
   mat_vec(out, g.mat, r);
   out[0] += g.pos[0]; out[1] += g.pos[1]; out[2] += g.pos[2];
+  return index;
 }
 
 struct Spt { float v[3], v1[3], v2[3]; };
@@ -955,30 +959,136 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
   quat_normalize(q);
   quat2mat(c.mat, q);
   c.size[0] = PKF(cg_size)[3 * cg]; c.size[1] = PKF(cg_size)[3 * cg + 1]; c.size[2] = PKF(cg_size)[3 * cg + 2];
-  c.verts = nullptr; c.nvert = 0; c.mesh = -1; c.soff = -1;
+  c.verts = nullptr; c.nvert = 0; c.mesh = -1; c.soff = -1; c.hadr = 0;
   if (c.type == GEOM_MESH) {
     int mid = PKI(cg_dataid)[cg];
-    c.verts = m.hull_vert + PKI(mesh_hulladr)[mid]; c.nvert = PKI(mesh_hullnum)[mid]; c.mesh = mid;
+    c.hadr = PKI(mesh_hulladr)[mid];
+    c.verts = m.hull_vert + c.hadr; c.nvert = PKI(mesh_hullnum)[mid]; c.mesh = mid;
   }
 }
 
 
-// analytic plane-vs-primitive routines and MPR for the rest; fills up to 4 contacts
-__device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, float margin, int so, int lane) {
-  // result record in shared memory, written by lane 0 (the computation is warp-uniform): count, normal[3], dist[4], pos[4][3]
+// Narrowphase result record in shared memory (written by lane 0; the computation is warp-uniform):
+//   [so] count, then per contact c at so + 4 + 8 c: normal[3], dist, pos[3], -.  Up to NP_MAXC contacts.
+// [so + 72, so + 96) is scratch for the unperturbed poses of the multiccd queries.
+#define NP_MAXC 8
+#define NP_EMIT(c, nx, ny, nz, dd, px, py, pz) do { if (w0) { float* o_ = smem + so + 4 + 8 * (c); \
+  o_[0] = (nx); o_[1] = (ny); o_[2] = (nz); o_[3] = (dd); o_[4] = (px); o_[5] = (py); o_[6] = (pz); } } while (0)
+
+// box-box [upstream mjc_BoxBox]: 15-axis separating-axis test, then the incident face clipped against the
+// reference face (up to 8 points) or one edge-edge point.  Same restatement as oracle/ss_oracle_collision.c:box_box.
+__device__ __noinline__ int box_box(const Cvx& A, const Cvx& B, float margin, int so, int lane) {
+  const bool w0 = lane == 0;
+  float a1[3][3], a2[3][3], pp[3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { a1[i][k] = A.mat[3 * k + i]; a2[i][k] = B.mat[3 * k + i]; }
+  for (int k = 0; k < 3; k++) pp[k] = B.pos[k] - A.pos[k];
+  const float *s1 = A.size, *s2 = B.size;
+  float bestf = -CUDART_INF_F, beste = -CUDART_INF_F, nf[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
+  int codef = -1, codee = -1;
+  for (int w = 0; w < 2; w++)
+    for (int i = 0; i < 3; i++) {
+      const float* L = w ? a2[i] : a1[i];
+      float t = dot3(pp, L), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += s1[k] * fabsf(dot3(a1[k], L)); rb += s2[k] * fabsf(dot3(a2[k], L)); }
+      float sep = fabsf(t) - ra - rb;
+      if (sep > margin) return 0;
+      if (sep > bestf) { bestf = sep; codef = 3 * w + i; float sg = t >= 0 ? 1.f : -1.f; nf[0] = L[0] * sg; nf[1] = L[1] * sg; nf[2] = L[2] * sg; }
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float L[3];
+      cross3(L, a1[i], a2[j]);
+      float len = sqrtf(dot3(L, L));
+      if (len < 1e-6f) continue;
+      float il = 1.0f / len;
+      L[0] *= il; L[1] *= il; L[2] *= il;
+      float t = dot3(pp, L), ra = 0, rb = 0;
+      for (int k = 0; k < 3; k++) { ra += s1[k] * fabsf(dot3(a1[k], L)); rb += s2[k] * fabsf(dot3(a2[k], L)); }
+      float sep = fabsf(t) - ra - rb;
+      if (sep > margin) return 0;
+      if (sep > beste) { beste = sep; codee = 3 * i + j; float sg = t >= 0 ? 1.f : -1.f; ne[0] = L[0] * sg; ne[1] = L[1] * sg; ne[2] = L[2] * sg; }
+    }
+  if (codee >= 0 && beste > bestf + 0.05f * fabsf(bestf) + 1e-9f) {
+    int i = codee / 3, j = codee % 3;
+    float c1[3] = {A.pos[0], A.pos[1], A.pos[2]}, c2[3] = {B.pos[0], B.pos[1], B.pos[2]};
+    for (int k = 0; k < 3; k++) {
+      if (k != i) { float sg = (dot3(ne, a1[k]) > 0 ? 1.f : -1.f) * s1[k]; c1[0] += a1[k][0] * sg; c1[1] += a1[k][1] * sg; c1[2] += a1[k][2] * sg; }
+      if (k != j) { float sg = (dot3(ne, a2[k]) > 0 ? -1.f : 1.f) * s2[k]; c2[0] += a2[k][0] * sg; c2[1] += a2[k][1] * sg; c2[2] += a2[k][2] * sg; }
+    }
+    float r[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]}, bb = dot3(a1[i], a2[j]), den = 1 - bb * bb;
+    float d1 = dot3(r, a1[i]), d2 = dot3(r, a2[j]);
+    float sA = den > 1e-12f ? (d1 - bb * d2) / den : 0.f, tB = den > 1e-12f ? (bb * d1 - d2) / den : 0.f;
+    NP_EMIT(0, ne[0], ne[1], ne[2], beste, 0.5f * (c1[0] + a1[i][0] * sA + c2[0] + a2[j][0] * tB),
+            0.5f * (c1[1] + a1[i][1] * sA + c2[1] + a2[j][1] * tB), 0.5f * (c1[2] + a1[i][2] * sA + c2[2] + a2[j][2] * tB));
+    return 1;
+  }
+  bool refis2 = codef >= 3;
+  int ax = codef % 3;
+  const float *pr = refis2 ? B.pos : A.pos, *sr = refis2 ? s2 : s1, *pc = refis2 ? A.pos : B.pos, *sc = refis2 ? s1 : s2;
+  float(*ar)[3] = refis2 ? a2 : a1;
+  float(*ac)[3] = refis2 ? a1 : a2;
+  float nr[3] = {refis2 ? -nf[0] : nf[0], refis2 ? -nf[1] : nf[1], refis2 ? -nf[2] : nf[2]};
+  int jc = 0; float bd = -1;
+  for (int k = 0; k < 3; k++) { float t = fabsf(dot3(ac[k], nr)); if (t > bd) { bd = t; jc = k; } }
+  float sgn = dot3(ac[jc], nr) > 0 ? -1.f : 1.f;
+  float fc[3] = {pc[0] + ac[jc][0] * sgn * sc[jc], pc[1] + ac[jc][1] * sgn * sc[jc], pc[2] + ac[jc][2] * sgn * sc[jc]};
+  int k1 = (jc + 1) % 3, k2 = (jc + 2) % 3, u = (ax + 1) % 3, v = (ax + 2) % 3;
+  float poly[16][2], tmp[16][2], hgt[4];
+  for (int c = 0; c < 4; c++) {
+    float e1 = (c == 0 || c == 3) ? -sc[k1] : sc[k1], e2 = c < 2 ? -sc[k2] : sc[k2];
+    float rel[3];
+    for (int k = 0; k < 3; k++) rel[k] = fc[k] + ac[k1][k] * e1 + ac[k2][k] * e2 - pr[k];
+    poly[c][0] = dot3(rel, ar[u]); poly[c][1] = dot3(rel, ar[v]); hgt[c] = dot3(rel, nr);
+  }
+  float e1x = poly[1][0] - poly[0][0], e1y = poly[1][1] - poly[0][1], e2x = poly[3][0] - poly[0][0], e2y = poly[3][1] - poly[0][1];
+  float dh1 = hgt[1] - hgt[0], dh2 = hgt[3] - hgt[0], det = e1x * e2y - e1y * e2x;
+  if (fabsf(det) < 1e-14f) return 0;
+  float gu = (dh1 * e2y - dh2 * e1y) / det, gv = (e1x * dh2 - e2x * dh1) / det;
+  float h0 = hgt[0] - gu * poly[0][0] - gv * poly[0][1];
+  int n = 4;
+  for (int pass = 0; pass < 4 && n > 0; pass++) {
+    int axis = pass >> 1;
+    float sign = (pass & 1) ? -1.f : 1.f, lim = axis ? sr[v] : sr[u];
+    int no = 0;
+    for (int i = 0; i < n; i++) {
+      const float *pa = poly[i], *pb = poly[(i + 1) % n];
+      float da = sign * pa[axis] - lim, db = sign * pb[axis] - lim;
+      if (da <= 0) { tmp[no][0] = pa[0]; tmp[no][1] = pa[1]; no++; }
+      if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+        float t = da / (da - db);
+        tmp[no][0] = pa[0] + t * (pb[0] - pa[0]); tmp[no][1] = pa[1] + t * (pb[1] - pa[1]); no++;
+      }
+    }
+    n = min(no, 8);
+    for (int i = 0; i < n; i++) { poly[i][0] = tmp[i][0]; poly[i][1] = tmp[i][1]; }
+  }
+  int cnt = 0;
+  for (int c = 0; c < n && cnt < NP_MAXC; c++) {
+    float h = h0 + gu * poly[c][0] + gv * poly[c][1], dist = h - sr[ax];
+    if (dist > margin) continue;
+    float hh = h - 0.5f * dist;
+    NP_EMIT(cnt, nf[0], nf[1], nf[2], dist, pr[0] + ar[u][0] * poly[c][0] + ar[v][0] * poly[c][1] + nr[0] * hh,
+            pr[1] + ar[u][1] * poly[c][0] + ar[v][1] * poly[c][1] + nr[1] * hh, pr[2] + ar[u][2] * poly[c][0] + ar[v][2] * poly[c][1] + nr[2] * hh);
+    cnt++;
+  }
+  return cnt;
+}
+
+// analytic plane-vs-primitive / box routines and MPR (+ multiccd) for the rest; fills up to NP_MAXC contacts.
+// mtol > 0: multiccd is on and mtol is the distinct-contact tolerance 1e-3 * min(rbound) [upstream mjc_Convex].
+__device__ __forceinline__ void narrow_pair_body(const DevModel& m, Cvx& A, Cvx& B, float margin, float mtol, int so, int lane) {
   const bool w0 = lane == 0;
   int& OC = reinterpret_cast<int&>(smem[so]);
-  float *ON = smem + so + 1, *OD = smem + so + 4, *OP = smem + so + 8;
   if (w0) OC = 0;
   if (A.type == GEOM_PLANE) {
     float n[3] = {A.mat[2], A.mat[5], A.mat[8]};
-    if (w0) ON[0] = n[0]; if (w0) ON[1] = n[1]; if (w0) ON[2] = n[2];
     float dif[3] = {B.pos[0] - A.pos[0], B.pos[1] - A.pos[1], B.pos[2] - A.pos[2]};
     if (B.type == GEOM_SPHERE) {
       float r = B.size[0], dist = dot3(dif, n) - r;
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) if (w0) OP[3 * 0 + k] = B.pos[k] - n[k] * (r + 0.5f * dist);
-      if (w0) OD[0] = dist; if (w0) OC = 1;
+      float t = r + 0.5f * dist;
+      NP_EMIT(0, n[0], n[1], n[2], dist, B.pos[0] - n[0] * t, B.pos[1] - n[1] * t, B.pos[2] - n[2] * t);
+      if (w0) OC = 1;
     } else if (B.type == GEOM_CYLINDER) {
       float axis[3] = {B.mat[2], B.mat[5], B.mat[8]}, vec[3];
       float r = B.size[0], h = B.size[1];
@@ -994,12 +1104,14 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
       float dist = dist0 + prjaxis + prjvec;
       if (dist > margin) return;
       int c = 0;
-      for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] + axis[k] - n[k] * dist * 0.5f;
-      { if (w0) OD[c] = dist; c++; }
+      NP_EMIT(c, n[0], n[1], n[2], dist, B.pos[0] + vec[0] + axis[0] - n[0] * dist * 0.5f, B.pos[1] + vec[1] + axis[1] - n[1] * dist * 0.5f,
+              B.pos[2] + vec[2] + axis[2] - n[2] * dist * 0.5f);
+      c++;
       dist = dist0 - prjaxis + prjvec;
       if (dist <= margin) {
-        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] - axis[k] - n[k] * dist * 0.5f;
-        { if (w0) OD[c] = dist; c++; }
+        NP_EMIT(c, n[0], n[1], n[2], dist, B.pos[0] + vec[0] - axis[0] - n[0] * dist * 0.5f, B.pos[1] + vec[1] - axis[1] - n[1] * dist * 0.5f,
+                B.pos[2] + vec[2] - axis[2] - n[2] * dist * 0.5f);
+        c++;
       }
       float prjvec1 = -prjvec * 0.5f;
       dist = dist0 + prjaxis + prjvec1;
@@ -1008,12 +1120,12 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         cross3(vec1, vec, axis); normalize3(vec1);
         float s = r * 0.8660254037844386f;
         vec1[0] *= s; vec1[1] *= s; vec1[2] *= s;
-        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-        { if (w0) OD[c] = dist; c++; }
-        if (c < 4) {
-          for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] - vec1[k] + axis[k] - vec[k] * 0.5f - n[k] * dist * 0.5f;
-          { if (w0) OD[c] = dist; c++; }
-        }
+        NP_EMIT(c, n[0], n[1], n[2], dist, B.pos[0] + vec1[0] + axis[0] - vec[0] * 0.5f - n[0] * dist * 0.5f,
+                B.pos[1] + vec1[1] + axis[1] - vec[1] * 0.5f - n[1] * dist * 0.5f, B.pos[2] + vec1[2] + axis[2] - vec[2] * 0.5f - n[2] * dist * 0.5f);
+        c++;
+        NP_EMIT(c, n[0], n[1], n[2], dist, B.pos[0] - vec1[0] + axis[0] - vec[0] * 0.5f - n[0] * dist * 0.5f,
+                B.pos[1] - vec1[1] + axis[1] - vec[1] * 0.5f - n[1] * dist * 0.5f, B.pos[2] - vec1[2] + axis[2] - vec[2] * 0.5f - n[2] * dist * 0.5f);
+        c++;
       }
       if (w0) OC = c;
     } else if (B.type == GEOM_BOX) {
@@ -1026,34 +1138,128 @@ __device__ __forceinline__ void narrow_pair_body(const Cvx& A, const Cvx& B, flo
         float ldist = dot3(n, vec);
         if (dist + ldist > margin || ldist > 0) continue;
         float cd = dist + ldist;
-        for (int k = 0; k < 3; k++) if (w0) OP[3 * c + k] = B.pos[k] + vec[k] - n[k] * cd * 0.5f;
-        { if (w0) OD[c] = cd; c++; }
+        NP_EMIT(c, n[0], n[1], n[2], cd, B.pos[0] + vec[0] - n[0] * cd * 0.5f, B.pos[1] + vec[1] - n[1] * cd * 0.5f, B.pos[2] + vec[2] - n[2] * cd * 0.5f);
+        c++;
       }
       if (w0) OC = c;
     } else if (B.type == GEOM_MESH) {
+      // [upstream mjc_PlaneConvex] support vertex + up to three of its hull neighbours within the margin
       float nd[3] = {-n[0], -n[1], -n[2]}, s[3];
-      support(B, nd, s, lane);
+      int v0 = support(B, nd, s, lane);
       float d3[3] = {s[0] - A.pos[0], s[1] - A.pos[1], s[2] - A.pos[2]};
       float dist = dot3(d3, n);
       if (dist > margin) return;
-      for (int k = 0; k < 3; k++) if (w0) OP[3 * 0 + k] = s[k] - n[k] * 0.5f * dist;
-      if (w0) OD[0] = dist; if (w0) OC = 1;
+      NP_EMIT(0, n[0], n[1], n[2], dist, s[0] - n[0] * 0.5f * dist, s[1] - n[1] * 0.5f * dist, s[2] - n[2] * 0.5f * dist);
+      int c = 1;
+      if (m.hull_edgeadr) {
+        int e0 = m.hull_edgeadr[B.hadr + v0], e1 = m.hull_edgeadr[B.hadr + v0 + 1];
+        for (int e = e0; e < e1 && c < 4; e++) {
+          float4 vl = B.verts[m.hull_edge[e]];
+          float l[3] = {vl.x, vl.y, vl.z}, w[3];
+          mat_vec(w, B.mat, l);
+          w[0] += B.pos[0]; w[1] += B.pos[1]; w[2] += B.pos[2];
+          float dd = (w[0] - A.pos[0]) * n[0] + (w[1] - A.pos[1]) * n[1] + (w[2] - A.pos[2]) * n[2];
+          if (dd > margin) continue;
+          NP_EMIT(c, n[0], n[1], n[2], dd, w[0] - n[0] * 0.5f * dd, w[1] - n[1] * 0.5f * dd, w[2] - n[2] * 0.5f * dd);
+          c++;
+        }
+      }
+      if (w0) OC = c;
     }
+  } else if (A.type == GEOM_BOX && B.type == GEOM_BOX) {
+    int c = box_box(A, B, margin, so, lane);
+    if (w0) OC = c;
+  } else if (A.type == GEOM_SPHERE && B.type == GEOM_BOX) {
+    // [upstream mjc_SphereBox] closest point of the box to the sphere centre
+    float dif[3] = {A.pos[0] - B.pos[0], A.pos[1] - B.pos[1], A.pos[2] - B.pos[2]}, cl[3], q[3], nl[3] = {0, 0, 0}, dist;
+    matT_vec(cl, B.mat, dif);
+    bool inside = true;
+    for (int k = 0; k < 3; k++) { q[k] = fminf(fmaxf(cl[k], -B.size[k]), B.size[k]); if (q[k] != cl[k]) inside = false; }
+    float r = A.size[0];
+    if (!inside) {
+      float dl[3] = {cl[0] - q[0], cl[1] - q[1], cl[2] - q[2]}, len = sqrtf(dot3(dl, dl));
+      dist = len - r;
+      if (dist > margin) return;
+      nl[0] = dl[0] / len; nl[1] = dl[1] / len; nl[2] = dl[2] / len;
+    } else {
+      int best = 0; float bd = CUDART_INF_F;
+      for (int k = 0; k < 3; k++) { float t = B.size[k] - fabsf(cl[k]); if (t < bd) { bd = t; best = k; } }
+      for (int k = 0; k < 3; k++) if (k == best) { nl[k] = cl[k] >= 0 ? 1.f : -1.f; q[k] = nl[k] * B.size[k]; }
+      dist = -bd - r;
+    }
+    float nw[3], qw[3];
+    mat_vec(nw, B.mat, nl); mat_vec(qw, B.mat, q);
+    NP_EMIT(0, -nw[0], -nw[1], -nw[2], dist, qw[0] + B.pos[0] + nw[0] * 0.5f * dist, qw[1] + B.pos[1] + nw[1] * 0.5f * dist,
+            qw[2] + B.pos[2] + nw[2] * 0.5f * dist);
+    if (w0) OC = 1;
   } else {
-    float depth, dir[3], pos[3];
-    if (!mpr_penetration(A, B, &depth, dir, pos, lane)) return;
-    if (dot3(dir, dir) < 0.5f) return;
-    if (w0) ON[0] = dir[0]; if (w0) ON[1] = dir[1]; if (w0) ON[2] = dir[2];
-    if (w0) OP[3 * 0 + 0] = pos[0]; if (w0) OP[3 * 0 + 1] = pos[1]; if (w0) OP[3 * 0 + 2] = pos[2];
-    if (w0) OD[0] = -depth; if (w0) OC = 1;
+    // [upstream mjc_Convex] one MPR query, then (multiccd, stretch.xml:8) four more with both geoms counter-rotated
+    // by +-1e-3 rad about the tangent axes of the first contact; a contact is kept when its position is farther
+    // than mtol from all contacts found so far.  One call site of mpr_penetration (code size).
+    bool multi = mtol > 0 && A.type != GEOM_SPHERE && A.type != GEOM_ELLIPSOID && B.type != GEOM_SPHERE && B.type != GEOM_ELLIPSOID;
+    float* P0 = smem + so + 72;   // unperturbed poses: A.pos, A.mat, B.pos, B.mat
+    float frame[9];
+    int cnt = 0;
+    for (int q = 0; q < (multi ? 5 : 1); q++) {
+      if (q == 1) {
+        __syncwarp();
+        if (w0) {
+          for (int k = 0; k < 3; k++) { P0[k] = A.pos[k]; P0[12 + k] = B.pos[k]; }
+          for (int k = 0; k < 9; k++) { P0[3 + k] = A.mat[k]; P0[15 + k] = B.mat[k]; }
+        }
+        __syncwarp();
+      }
+      if (q >= 1) {
+        const float* ax = frame + 3 + 3 * ((q - 1) >> 1);
+        const float sn = ((q - 1) & 1) ? 4.99999979e-4f : -4.99999979e-4f, cs = 0.999999875f;   // sin, cos of 1e-3 / 2
+        float qr[4] = {cs, ax[0] * sn, ax[1] * sn, ax[2] * sn}, R[9];
+        quat2mat(R, qr);
+        const float* org = smem + so + 4 + 4;   // position of the first contact
+        float o3[3] = {org[0], org[1], org[2]};
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            A.mat[3 * r + c] = R[3 * r] * P0[3 + c] + R[3 * r + 1] * P0[6 + c] + R[3 * r + 2] * P0[9 + c];
+            B.mat[3 * r + c] = R[r] * P0[15 + c] + R[3 + r] * P0[18 + c] + R[6 + r] * P0[21 + c];
+          }
+        float ra[3] = {P0[0] - o3[0], P0[1] - o3[1], P0[2] - o3[2]}, rb[3] = {P0[12] - o3[0], P0[13] - o3[1], P0[14] - o3[2]}, t[3];
+        mat_vec(t, R, ra); A.pos[0] = o3[0] + t[0]; A.pos[1] = o3[1] + t[1]; A.pos[2] = o3[2] + t[2];
+        matT_vec(t, R, rb); B.pos[0] = o3[0] + t[0]; B.pos[1] = o3[1] + t[1]; B.pos[2] = o3[2] + t[2];
+      }
+      float depth, dir[3], pos[3];
+      bool hit = mpr_penetration(A, B, &depth, dir, pos, lane) && dot3(dir, dir) >= 0.5f;
+      if (q == 0) {
+        if (!hit) return;
+        frame[0] = dir[0]; frame[1] = dir[1]; frame[2] = dir[2];
+        float* y = frame + 3;
+        y[0] = 0; y[1] = 1; y[2] = 0;
+        if (dir[1] > 0.5f || dir[1] < -0.5f) { y[1] = 0; y[2] = 1; }
+        float d = dot3(dir, y);
+        y[0] -= dir[0] * d; y[1] -= dir[1] * d; y[2] -= dir[2] * d;
+        normalize3(y);
+        cross3(frame + 6, dir, y);
+      } else {
+        if (!hit) continue;
+        bool distinct = true;
+        for (int k = 0; k < cnt; k++) {
+          const float* pk = smem + so + 4 + 8 * k + 4;
+          float dx = pk[0] - pos[0], dy = pk[1] - pos[1], dz = pk[2] - pos[2];
+          if (dx * dx + dy * dy + dz * dz < mtol * mtol) distinct = false;
+        }
+        if (!distinct) continue;
+      }
+      NP_EMIT(cnt, dir[0], dir[1], dir[2], margin - depth, pos[0], pos[1], pos[2]);
+      cnt++;
+      if (w0) OC = cnt;
+      __syncwarp();
+    }
   }
 }
 
 // Single noinline body of the narrowphase; the operands are copied into registers once (they arrive through
 // local memory) and everything below (MPR, support scans) is inlined so that they stay there.
-__device__ __noinline__ void narrow_pair(const Cvx& A_, const Cvx& B_, float margin, int so, int lane) {
-  const Cvx A = A_, B = B_;
-  narrow_pair_body(A, B, margin, so, lane);
+__device__ __noinline__ void narrow_pair(const DevModel& m, const Cvx& A_, const Cvx& B_, float margin, float mtol, int so, int lane) {
+  Cvx A = A_, B = B_;
+  narrow_pair_body(m, A, B, margin, mtol, so, lane);
   __syncwarp();
 }
 
@@ -1207,21 +1413,21 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       make_cvx(m, S, c1, A);
       make_cvx(m, S, c2, B);
       if (A.type != GEOM_PLANE) stage_pair(hs, A, B, lane);
-      narrow_pair(A, B, m.pair_margin[pair], so, lane);
+      narrow_pair(m, A, B, m.pair_margin[pair], m.multiccd ? 1e-3f * fminf(PKF(cg_rbound)[c1], PKF(cg_rbound)[c2]) : 0.f, so, lane);
       const int ocount = __float_as_int(smem[so]);
-      const float *on = smem + so + 1, *od = smem + so + 4, *op = smem + so + 8;
       for (int c = 0; c < ocount; c++) {
         if (ncon >= m.maxcon) { flags |= 2; break; }
         if (lane == 0) {
           float* cr = S + o.con + ncon * CON_STRIDE;
-          float x[3] = {on[0], on[1], on[2]}, y[3] = {0, 1, 0}, z[3];
+          const float* rec = smem + so + 4 + 8 * c;
+          float x[3] = {rec[0], rec[1], rec[2]}, y[3] = {0, 1, 0}, z[3];
           if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
           float d = dot3(x, y);
           y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
           normalize3(y);
           cross3(z, x, y);
-          for (int k = 0; k < 3; k++) { cr[C_POS + k] = op[3 * c + k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
-          cr[C_DIST] = od[c]; cr[C_MU] = 0;
+          for (int k = 0; k < 3; k++) { cr[C_POS + k] = rec[4 + k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
+          cr[C_DIST] = rec[3]; cr[C_MU] = 0;
           cr[C_DIM] = __int_as_float(m.pair_condim[pair]); cr[C_PAIR] = __int_as_float(pair); cr[C_EFC] = __int_as_float(-1);
           cr[C_BODY1] = __int_as_float(PKI(cg_bodyid)[c1]); cr[C_BODY2] = __int_as_float(PKI(cg_bodyid)[c2]);
           for (int k = 0; k < 5; k++) cr[C_FRICTION + k] = m.pair_friction[5 * pair + k];
