@@ -32,7 +32,11 @@ extern "C" const char* ss_version(void) { return "stretchsim 0.1.0 (sm_100a)"; }
     if (e_ != cudaSuccess) return ss_fail("%s: %s", #x, cudaGetErrorString(e_));        \
   } while (0)
 
-extern "C" __global__ void ss_physics_kernel(DevModel m, StepArgs a);
+extern "C" __global__ void ss_smooth_kernel(DevModel m, StepArgs a);
+extern "C" __global__ void ss_narrow_kernel(DevModel m, StepArgs a);
+extern "C" __global__ void ss_solve_kernel(DevModel m, StepArgs a);
+#define NP_SMEM 96   // floats of shared memory per warp of the narrowphase kernel (physics.cu)
+#define NARROW_THREADS 256
 
 // Env visiting order for the next physics launch: counting sort of the envs by the cost they reported in
 // the LAST step of the previous launch (Newton iterations + narrowphase queries), heaviest first.  An env's
@@ -43,7 +47,7 @@ __global__ void schedule_kernel(int env0, int nenv, const int32_t* __restrict__ 
                                 int32_t* __restrict__ work_counter) {   // envs [env0, env0 + nenv) -> order[0 .. nenv)
   cost += env0;
   __shared__ int hist[256], start[256];
-  if (threadIdx.x == 0) *work_counter = 0;
+  if (threadIdx.x < 4) work_counter[threadIdx.x] = 0;   // solve-kernel work counter, narrowphase item count / fetch counter, spare
   if (mode < 0) {  // SS_NOSORT=1: identity order (A/B knob)
     for (int e = threadIdx.x; e < nenv; e += blockDim.x) order[e] = env0 + e;
     return;
@@ -87,36 +91,37 @@ static std::vector<int> i32(const ss_blob& b, const char* name) {
   return std::vector<int>(p, p + n);
 }
 
-static int build_layout(DevModel& m) {
+// kernel: 1 = smooth kernel (persistent block + kinematics / dynamics scratch), 3 = solve kernel (persistent
+// block + constraint rows + solver scratch).  The persistent block has the same offsets in both.
+static int build_layout(DevModel& m, int kernel) {
   EnvLayout& o = m.L;
+  memset(&o, 0, sizeof(o));
   int off = 0;
   auto take = [&](int n) { int r = off; off += (n + 3) & ~3; return r; };
   int nv = m.nv, nb = m.nbody;
   o.ldm = nv <= 32 ? ((nv + 3) & ~3) : (nv | 1);   // n <= 32: float4 rows (register Cholesky path); else odd stride (scalar, conflict-free)
   o.ldj = (nv + 3) & ~3;   // 16-byte aligned rows (float4 operand loads in the Hessian build)
-  // live for the whole step
-  o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv); o.qacc = take(nv);
+  o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv);
   o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.cdof = take(nv * 6); o.cdofdot = take(nv * 6); o.cvel = take(nb * 6);
   o.M = take(nv * o.ldm);
-  o.qfrc_smooth = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
-  o.actforce = take(m.nu); o.actlen = take(m.nu); o.actvel = take(m.nu);
-  o.con = take(m.maxcon * CON_STRIDE);
-  o.s_d1 = take(m.maxsimple); o.s_c1 = take(m.maxsimple); o.s_d2 = take(m.maxsimple); o.s_c2 = take(m.maxsimple);
-  o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxrow); o.e_info = take(m.maxrow);
-  o.J = take(m.maxcrow * o.ldj);
-  // region X (kinematics / dynamics scratch) and region Y (solver scratch) share the tail
-  int base = off;
-  o.xmat = take(nb * 9); o.cinert = take(nb * 10);
-  o.cacc = take(nb * 6); o.cfrc = take(nb * 6);
-  o.crb = o.cacc;                      // composite inertias (10/body) die before cacc/cfrc (6+6/body) are born
+  o.qfrc_smooth = take(nv); o.actforce = take(m.nu); o.actlen = take(m.nu); o.actvel = take(m.nu);
   o.gpos = take(m.ncgeom * 3);
-  int endX = off;
-  off = base;
-  o.H = take(nv * o.ldm); o.tmpJ = take(6 * o.ldj);
-  o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
-  o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
-  int endY = off;
-  off = std::max(endX, endY);
+  o.pb = off;
+  if (kernel == 1) {
+    o.xmat = take(nb * 9); o.cinert = take(nb * 10);
+    o.cacc = take(nb * 10); o.cfrc = take(nb * 6);
+    o.crb = o.cacc;                      // composite inertias (10/body) die before the RNE accelerations (6/body) are born
+  } else {
+    o.qacc = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
+    o.con = take(m.maxcon * CON_STRIDE);
+    o.s_d1 = take(m.maxsimple); o.s_c1 = take(m.maxsimple); o.s_d2 = take(m.maxsimple); o.s_c2 = take(m.maxsimple);
+    o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxrow); o.e_info = take(m.maxrow);
+    o.J = take(m.maxcrow * o.ldj);
+    o.H = take(nv * o.ldm); o.tmpJ = take(6 * o.ldj);
+    o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
+    o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
+    o.cacc = take(nb * 6);
+  }
   o.total = off;
   return off;
 }
@@ -385,31 +390,44 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   int nsimple = m.neq + m.nfloss + 2 * m.nlimited;
   m.maxsimple = nsimple;
   m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 96;
-  if (const char* e = getenv("SS_MAXCROW")) m.maxcrow = atoi(e);
-  if (const char* e = getenv("SS_MAXCON")) m.maxcon = atoi(e);
   m.maxrow = m.maxsimple + m.maxcrow;
-  int floats = build_layout(m);
-  B->smem_per_env = (size_t)floats * sizeof(float);
+  B->dm1 = m;
+  B->smem_per_env = (size_t)build_layout(m, 3) * sizeof(float);
+  B->smem_per_env1 = (size_t)build_layout(B->dm1, 1) * sizeof(float);
+  B->pb_stride = m.L.pb;
   cudaSetDevice(M->device);
   int max_smem = 0, sms = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
   size_t pack_bytes = (size_t)m.pk.nwords * 4 + 2048;  // + static shared (mbarrier, compiler scratch) slack
   int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
-  if (wpb < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
-  wpb = std::min(wpb, 8);   // __launch_bounds__(256, 1): up to 255 registers per thread
-  if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs
-  B->sync_level = 9;   // stage barriers (1) + CTA-uniform Newton loop (8), see physics.cu
+  int wpb1 = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env1) : 0;
+  if (wpb < 1 || wpb1 < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
+  wpb = std::min(wpb, 8);     // ss_solve_kernel: __launch_bounds__(256, 1), up to 255 registers per thread
+  wpb1 = std::min(wpb1, 16);  // ss_smooth_kernel: __launch_bounds__(512, 1)
+  if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs (A/B experiments; results never depend on them)
+  if (const char* e = getenv("SS_WPB1")) wpb1 = std::max(1, std::min(wpb1, atoi(e)));
+  B->sync_level = 9;   // 1: stage barriers in the smooth kernel, 8: lockstep Newton loop in the solve kernel (physics.cu)
   if (const char* e = getenv("SS_SYNC")) B->sync_level = atoi(e);
   B->group_warps = 0;
-  if (const char* e = getenv("SS_GROUP")) B->group_warps = atoi(e);
   B->pack_bytes = (size_t)m.pk.nwords * 4;
-  B->warps_per_block = wpb;
+  B->warps_per_block = wpb; B->warps_per_block1 = wpb1;
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
-  cudaError_t e = cudaFuncSetAttribute(ss_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B->pack_bytes + wpb * B->smem_per_env));
-  if (e != cudaSuccess) { delete B; return ss_fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  B->grid1 = std::min((nenv + wpb1 - 1) / wpb1, sms);
+  B->grid2 = 2 * sms;
+  // pipeline scratch: persistent blocks, broadphase slots, narrowphase records, work-item queue
+  B->maxslot = std::max(32, 2 * m.maxcon);
+  if (const char* e = getenv("SS_MAXSLOT")) B->maxslot = std::max(8, atoi(e));
+  size_t nslot = (size_t)nenv * B->maxslot;
+  if (cudaMalloc((void**)&B->pb, sizeof(float) * (size_t)nenv * B->pb_stride) != cudaSuccess ||
+      cudaMalloc((void**)&B->rec, sizeof(float) * nslot * NP_REC) != cudaSuccess ||
+      cudaMalloc((void**)&B->npass, sizeof(int32_t) * nenv) != cudaSuccess || cudaMalloc((void**)&B->slot_pair, sizeof(int32_t) * nslot) != cudaSuccess ||
+      cudaMalloc((void**)&B->items, sizeof(int32_t) * nslot) != cudaSuccess || cudaMemset(B->npass, 0, sizeof(int32_t) * nenv) != cudaSuccess) {
+    ss_batch_free(B);
+    return ss_fail("ss_batch_create: pipeline scratch: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   if (cudaMalloc((void**)&B->order, sizeof(int32_t) * nenv) != cudaSuccess || cudaMalloc((void**)&B->cost, sizeof(int32_t) * nenv) != cudaSuccess ||
-      cudaMalloc((void**)&B->work_counter, sizeof(int32_t) * SS_MAXSETS) != cudaSuccess || cudaMemset(B->cost, 0, sizeof(int32_t) * nenv) != cudaSuccess) {
+      cudaMalloc((void**)&B->work_counter, sizeof(int32_t) * 4 * SS_MAXSETS) != cudaSuccess || cudaMemset(B->cost, 0, sizeof(int32_t) * nenv) != cudaSuccess) {
     ss_batch_free(B);
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -438,6 +456,11 @@ extern "C" void ss_batch_free(ss_batch* B) {
   if (!B) return;
   cudaSetDevice(B->model->device);
   if (B->ray_xf) cudaFree(B->ray_xf);
+  if (B->pb) cudaFree(B->pb);
+  if (B->rec) cudaFree(B->rec);
+  if (B->npass) cudaFree(B->npass);
+  if (B->slot_pair) cudaFree(B->slot_pair);
+  if (B->items) cudaFree(B->items);
   if (B->order) cudaFree(B->order);
   if (B->cost) cudaFree(B->cost);
   if (B->work_counter) cudaFree(B->work_counter);
@@ -471,30 +494,41 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   cudaSetDevice(B->model->device);
   B->dm.iterations = B->model->dm.iterations;  // runtime-settable solver options (ss_model_set)
   B->dm.tolerance = B->model->dm.tolerance;
-  size_t smem = B->pack_bytes + B->warps_per_block * B->smem_per_env;
-  a.order = B->order; a.cost = B->cost; a.work_counter = B->work_counter;
-  // Short launches, re-sorted in between (see schedule_kernel); observations come from the last one.
-  // The env batch is cut into `nsets` contiguous sets whose launch chains run on library-owned side
-  // streams, forked from and joined back into the caller's stream by events: the persistent CTAs of one
-  // set drain while the next set's CTAs take over the freed SMs, which hides the tail of every launch.
+  a.cost = B->cost;
+  a.pb = B->pb; a.pb_stride = B->pb_stride; a.maxslot = B->maxslot; a.npass = B->npass; a.slot_pair = B->slot_pair; a.rec = B->rec;
+  // dynamic shared memory is per-function state shared by all batches of the process: set it before every
+  // launch chain (a batch created later with a smaller footprint must not lower it for this one)
+  const size_t smem1 = B->pack_bytes + B->warps_per_block1 * B->smem_per_env1, smem3 = B->pack_bytes + B->warps_per_block * B->smem_per_env;
+  const size_t smem2 = B->pack_bytes + (NARROW_THREADS / 32) * NP_SMEM * sizeof(float);
+  CUDA_OK(cudaFuncSetAttribute(ss_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  CUDA_OK(cudaFuncSetAttribute(ss_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  CUDA_OK(cudaFuncSetAttribute(ss_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  // One mj_step = schedule_kernel (cost-sorted env order, counters) -> ss_smooth_kernel -> ss_narrow_kernel ->
+  // ss_solve_kernel.  The env batch is cut into `nsets` contiguous sets whose launch chains run on library-owned
+  // side streams, forked from and joined back into the caller's stream by events: one set's kernels fill the SMs
+  // that the other set's tails leave idle.
   const int cost_scale = B->cost_scale;
   cudaStream_t user = (cudaStream_t)stream;
-  int chunk = forward_only ? 1 : B->steps_per_launch;
-  int nsets = (forward_only || nsteps <= chunk) ? 1 : B->nsets;
+  int nsets = (forward_only || nsteps < 2) ? 1 : B->nsets;
   if (nsets > 1) {
     CUDA_OK(cudaEventRecord(B->ev_fork, user));
     for (int k = 0; k < nsets; k++) CUDA_OK(cudaStreamWaitEvent(B->side[k], B->ev_fork, 0));
   }
-  for (int done = 0; done < nsteps; done += chunk) {
-    a.nsteps = std::min(chunk, nsteps - done);
+  a.nsteps = 1;
+  for (int done = 0; done < nsteps; done++) {
     for (int k = 0; k < nsets; k++) {
       int e0 = (int)((long)B->nenv * k / nsets), e1 = (int)((long)B->nenv * (k + 1) / nsets);
       cudaStream_t st = nsets > 1 ? B->side[k] : user;
-      a.nenv = e1 - e0; a.order = B->order + e0; a.work_counter = B->work_counter + k;
-      int grid = std::min((a.nenv + B->warps_per_block - 1) / B->warps_per_block, B->grid);
-      schedule_kernel<<<1, 1024, 0, st>>>(e0, a.nenv, B->cost, B->nosort ? -1 : 0, cost_scale, B->order + e0, B->work_counter + k);
-      ss_physics_kernel<<<grid, B->warps_per_block * 32, smem, st>>>(B->dm, a);
-      B->launches += 2;
+      a.nenv = e1 - e0; a.order = B->order + e0;
+      a.work_counter = B->work_counter + 4 * k; a.item_count = a.work_counter + 1; a.item_next = a.work_counter + 2;
+      a.items = B->items + (size_t)e0 * B->maxslot;
+      schedule_kernel<<<1, 1024, 0, st>>>(e0, a.nenv, B->cost, B->nosort ? -1 : 0, cost_scale, B->order + e0, a.work_counter);
+      int g1 = std::min((a.nenv + B->warps_per_block1 - 1) / B->warps_per_block1, B->grid1);
+      int g3 = std::min((a.nenv + B->warps_per_block - 1) / B->warps_per_block, B->grid);
+      ss_smooth_kernel<<<g1, B->warps_per_block1 * 32, smem1, st>>>(B->dm1, a);
+      ss_narrow_kernel<<<B->grid2, NARROW_THREADS, smem2, st>>>(B->dm1, a);
+      ss_solve_kernel<<<g3, B->warps_per_block * 32, smem3, st>>>(B->dm, a);
+      B->launches += 4;
     }
   }
   if (nsets > 1)

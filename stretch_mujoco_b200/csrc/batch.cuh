@@ -16,4 +16,13 @@ struct StepArgs {
   // scheduling (library-owned): env visiting order (heaviest first), per-env cost of this launch, CTA work counter
   const int32_t* order;
   int32_t *cost, *work_counter;
+  // pipeline scratch (library-owned)
+  float* pb;               // [nenv, pb_stride] persistent block of every env (smooth kernel -> narrowphase / solve kernels)
+  int pb_stride, maxslot;
+  int32_t* npass;          // [nenv] candidate pairs that passed the broadphase
+  int32_t* slot_pair;      // [nenv, maxslot] their pair ids, reference order
+  float* rec;              // [nenv, maxslot, NP_REC] narrowphase records: count, then 8 floats per contact
+  int32_t* items;          // work-item queue of the narrowphase kernel (env * maxslot + slot)
+  int32_t *item_count, *item_next;
 };
+#define NP_REC 72

@@ -29,9 +29,13 @@ struct ss_batch {
   int nenv;
   ss_buffers bufs;
   ss_debug_buffers dbg;
-  DevModel dm;  // model + this batch's buffer sizes and shared-memory layout
-  size_t smem_per_env, pack_bytes;
-  int warps_per_block, grid, sync_level, group_warps;
+  DevModel dm;   // model + this batch's buffer sizes and the SOLVE kernel's shared-memory layout
+  DevModel dm1;  // same with the SMOOTH kernel's layout (also used by the narrowphase kernel: persistent block only)
+  size_t smem_per_env, smem_per_env1, pack_bytes;
+  int warps_per_block, warps_per_block1, grid, grid1, grid2, sync_level, group_warps;
+  int maxslot = 0, pb_stride = 0;
+  float *pb = nullptr, *rec = nullptr;
+  int32_t *npass = nullptr, *slot_pair = nullptr, *items = nullptr, *counters = nullptr;   // counters: 4 ints per env set
   long launches;
   int steps_per_launch = 1;   // long rollouts are cut into launches of this many steps, re-sorted in between
   bool nosort = false;

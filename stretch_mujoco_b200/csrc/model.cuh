@@ -19,21 +19,27 @@ enum { SENS_GYRO = 0, SENS_ACCEL = 1, SENS_RANGE = 2 };
 enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION, CNSTR_LIMIT, CNSTR_CONTACT_FRICTIONLESS, CNSTR_CONTACT_ELLIPTIC };
 enum { ST_SATISFIED = 0, ST_QUADRATIC, ST_LINEARNEG, ST_LINEARPOS, ST_CONE };
 
-// Shared-memory layout of one env (offsets in floats from the env's slice), computed on the host.
-// Region X (kinematics/dynamics scratch) is dead once the constraint rows are assembled and is
-// overlaid by region Y (solver scratch): see build_layout() in api.cu.
+// Shared-memory layout of one env (offsets in floats from the env's slice), computed on the host
+// (api.cu:build_layout), one layout per kernel.  All layouts start with the same "persistent block"
+// [0, pb): the fields that travel from the smooth kernel to the narrowphase and solve kernels through
+// global memory (one contiguous float4 copy per env).
 struct EnvLayout {
-  int qpos, qvel, ctrl, warm, qacc;
-  int xpos, xquat, cdof, cdofdot, cvel;          // live for the whole step (needed by sensors / outputs)
-  int M, ldm;                                    // dense nv x nv joint-space inertia, row stride ldm (odd)
-  int qfrc_smooth, qacc_smooth, qfrc_con, actforce, actlen, actvel;
+  // persistent block
+  int qpos, qvel, ctrl, warm;
+  int xpos, xquat, cdof, cdofdot, cvel;
+  int M, ldm;                                    // dense nv x nv joint-space inertia, row stride ldm
+  int qfrc_smooth, actforce, actlen, actvel;
+  int gpos;                                      // world positions of the collision geoms
+  int pb;                                        // size of the persistent block (multiple of 4)
+  // smooth kernel only
+  int xmat, cinert, crb, cfrc;
+  int cacc;                                      // smooth kernel: RNE accelerations; solve kernel: rebuilt with qacc for the IMU
+  // solve kernel only
+  int qacc, qacc_smooth, qfrc_con;
   int con;                                       // contacts [maxcon * CON_STRIDE]
   int s_d1, s_c1, s_d2, s_c2;                    // simple rows (equality, friction loss, limit): <=2 non-zeros
   int e_R, e_D, e_aref, e_floss, e_info;         // all rows [maxrow]; e_info packs type | state<<4 | id<<8
   int J, ldj;                                    // dense Jacobian of CONTACT rows [maxcrow * ldj]
-  // region X
-  int xmat, cinert, crb, cacc, cfrc, gpos;
-  // region Y (overlays X)
   int H, tmpJ, e_force, e_jar, e_jv, v_Ma, v_grad, v_search, v_mv, v_tmp;
   int total;
 };

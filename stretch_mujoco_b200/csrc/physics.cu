@@ -1,11 +1,14 @@
-// Physics kernel of libstretchsim: nsteps x mj_step for a batch of independent envs.
+// Physics kernels of libstretchsim: one mj_step for a batch of independent envs.
 //
 // Replaces the reference's per-step call `mujoco.mj_step(model, data)`
-// (stretch_mujoco/mujoco_server.py:378) -- stages S1..S10 of SURVEY.md §8(a) -- with ONE
-// persistent sm_100a kernel: one warp owns one env, the env's whole working set lives in that
-// warp's slice of shared memory for all nsteps, and HBM is touched only to load the state and
-// ctrl at the start and to store state + observations at the end (828 B/env-step algorithmic).
-// The model's small tables are pulled into shared memory once per CTA by a TMA bulk copy.
+// (stretch_mujoco/mujoco_server.py:378) -- stages S1..S10 of SURVEY.md §8(a) -- with a pipeline of
+// three sm_100a kernels per step (csrc/api.cu:launch_physics):
+//   ss_smooth_kernel  one warp per env: kinematics, CRBA, broadphase, velocity / RNE, actuation (S1, S3, S5)
+//   ss_narrow_kernel  one warp per candidate geom pair of any env: narrowphase (S1c), balanced over the chip
+//   ss_solve_kernel   one warp per env: constraint rows, Newton solver, sensors, implicitfast (S1m, S4, S6..S10)
+// An env's working set lives in its warp's slice of shared memory inside a kernel and travels between
+// kernels as one contiguous "persistent block" per env in global memory (L2 resident).  The model's small
+// tables are pulled into shared memory once per CTA by a TMA bulk copy.
 //
 // Lane mapping: lane = dof for joint-space vectors and matrix rows, lane = body inside one tree
 // level for the kinematic passes, lane = constraint row / contact for the solver's row passes.
@@ -703,7 +706,7 @@ __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int
 
 // ----------------------------------------------------------------------------- S1c: collision
 struct Cvx {
-  int type, nvert, mesh, soff;   // soff: float4 index of the staged hull in shared memory, -1 = not staged
+  int type, nvert;
   int hadr;                      // first hull vertex of the mesh in hull_vert / hull_edgeadr
   float pos[3], mat[9], size[3];
   const float4* verts;
@@ -758,36 +761,33 @@ __device__ __forceinline__ int support(const Cvx& g, const float* dir, float* ou
 struct Spt { float v[3], v1[3], v2[3]; };
 
 // Minkowski-difference support: both geoms are scanned in ONE loop so that the two vertex streams and
-// the two reductions overlap (the MPR iteration is a dependent chain of these calls).  SH = every mesh
-// operand is staged in shared memory (stage_pair): vertices come through LDS instead of generic loads.
-template <bool SH>
+// the two reductions overlap (the MPR iteration is a dependent chain of these calls).  Hull vertices are
+// read-only float4 loads that live in L1 / L2 (229 KB for the robot's 65 hulls).
 __device__ __forceinline__ void msupport_scan(const Cvx& a, const Cvx& b, int na, int nb, const float* la, const float* lb, float* ra,
                                               float* rb, int lane) {
-  const float4* sm4 = reinterpret_cast<const float4*>(smem);
   float besta = -CUDART_INF_F, bestb = -CUDART_INF_F; int bia = 0x7fffffff, bib = 0x7fffffff;
 #pragma unroll 2
   for (int i = lane; i < max(na, nb); i += 32) {
     if (i < na) {
-      float4 v = SH ? sm4[a.soff + i] : a.verts[i];
+      float4 v = __ldg(a.verts + i);
       float t = v.x * la[0] + v.y * la[1] + v.z * la[2];
       if (t > besta) { besta = t; bia = i; }
     }
     if (i < nb) {
-      float4 v = SH ? sm4[b.soff + i] : b.verts[i];
+      float4 v = __ldg(b.verts + i);
       float t = v.x * lb[0] + v.y * lb[1] + v.z * lb[2];
       if (t > bestb) { bestb = t; bib = i; }
     }
   }
-  if (na) { int k = warp_argmax(besta, bia); float4 v = SH ? sm4[a.soff + k] : a.verts[k]; ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; }
-  if (nb) { int k = warp_argmax(bestb, bib); float4 v = SH ? sm4[b.soff + k] : b.verts[k]; rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; }
+  if (na) { int k = warp_argmax(besta, bia); float4 v = __ldg(a.verts + k); ra[0] = v.x; ra[1] = v.y; ra[2] = v.z; }
+  if (nb) { int k = warp_argmax(bestb, bib); float4 v = __ldg(b.verts + k); rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; }
 }
 __device__ __forceinline__ void msupport(const Cvx& a, const Cvx& b, const float* dir, Spt& s, int lane) {
   float nd[3] = {-dir[0], -dir[1], -dir[2]}, la[3], lb[3], ra[3], rb[3];
   matT_vec(la, a.mat, dir);
   matT_vec(lb, b.mat, nd);
   int na = a.type == GEOM_MESH ? a.nvert : 0, nb = b.type == GEOM_MESH ? b.nvert : 0;
-  if ((na == 0 || a.soff >= 0) && (nb == 0 || b.soff >= 0)) msupport_scan<true>(a, b, na, nb, la, lb, ra, rb, lane);
-  else msupport_scan<false>(a, b, na, nb, la, lb, ra, rb, lane);
+  if (na | nb) msupport_scan(a, b, na, nb, la, lb, ra, rb, lane);
   if (!na) support_prim(a, la, ra);
   if (!nb) support_prim(b, lb, rb);
   mat_vec(s.v1, a.mat, ra);
@@ -948,7 +948,7 @@ __device__ __forceinline__ bool mpr_penetration(const Cvx& A, const Cvx& B, floa
   return false;
 }
 
-__device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int cg, Cvx& c) {
+__device__ __forceinline__ void make_cvx(const DevModel& m, const float* __restrict__ S, int cg, Cvx& c) {
   const EnvLayout& o = m.L;
   int b = PKI(cg_bodyid)[cg];
   c.type = PKI(cg_type)[cg];
@@ -959,11 +959,11 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
   quat_normalize(q);
   quat2mat(c.mat, q);
   c.size[0] = PKF(cg_size)[3 * cg]; c.size[1] = PKF(cg_size)[3 * cg + 1]; c.size[2] = PKF(cg_size)[3 * cg + 2];
-  c.verts = nullptr; c.nvert = 0; c.mesh = -1; c.soff = -1; c.hadr = 0;
+  c.verts = nullptr; c.nvert = 0; c.hadr = 0;
   if (c.type == GEOM_MESH) {
     int mid = PKI(cg_dataid)[cg];
     c.hadr = PKI(mesh_hulladr)[mid];
-    c.verts = m.hull_vert + c.hadr; c.nvert = PKI(mesh_hullnum)[mid]; c.mesh = mid;
+    c.verts = m.hull_vert + c.hadr; c.nvert = PKI(mesh_hullnum)[mid];
   }
 }
 
@@ -972,6 +972,7 @@ __device__ __forceinline__ void make_cvx(const DevModel& m, const float* S, int 
 //   [so] count, then per contact c at so + 4 + 8 c: normal[3], dist, pos[3], -.  Up to NP_MAXC contacts.
 // [so + 72, so + 96) is scratch for the unperturbed poses of the multiccd queries.
 #define NP_MAXC 8
+#define NP_SMEM 96   // floats of shared memory per warp of the narrowphase kernel (record + multiccd scratch)
 #define NP_EMIT(c, nx, ny, nz, dd, px, py, pz) do { if (w0) { float* o_ = smem + so + 4 + 8 * (c); \
   o_[0] = (nx); o_[1] = (ny); o_[2] = (nz); o_[3] = (dd); o_[4] = (px); o_[5] = (py); o_[6] = (pz); } } while (0)
 
@@ -1263,55 +1264,10 @@ __device__ __noinline__ void narrow_pair(const DevModel& m, const Cvx& A_, const
   __syncwarp();
 }
 
-// Hull staging: MPR calls the support function of both hulls 20-60 times per query, each call a
-// scan over all hull vertices.  Instead of scanning them in global memory (L2 latency per call; the
-// L1 is carved down to ~30 KB by the shared-memory working sets) the pair's hulls are pulled once
-// into the env's not-yet-used Jacobian region by TMA bulk copies that complete on a per-warp
-// mbarrier.  Slot A (offset 0) is reused while consecutive pairs share their first geom.
-struct HullStage { float4* buf; int cap, soff; unsigned bar; unsigned phase; int resA, nA; };
-
-__device__ __forceinline__ void stage_pair(HullStage& hs, Cvx& A, Cvx& B, int lane) {
-  bool needA = A.type == GEOM_MESH && A.nvert <= hs.cap && A.mesh != hs.resA;
-  if (A.type == GEOM_MESH && A.nvert > hs.cap) { hs.resA = -1; hs.nA = 0; }
-  if (A.type != GEOM_MESH) { hs.resA = -1; hs.nA = 0; }
-  if (needA) { hs.resA = A.mesh; hs.nA = A.nvert; }
-  bool stA = A.type == GEOM_MESH && hs.resA == A.mesh;
-  int offB = stA ? hs.nA : 0;
-  bool stB = B.type == GEOM_MESH && B.nvert <= hs.cap - offB;
-  unsigned bytes = (needA ? A.nvert * 16u : 0u) + (stB ? B.nvert * 16u : 0u);
-  if (bytes) {
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hs.bar), "r"(bytes) : "memory");
-      if (needA)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         (unsigned)__cvta_generic_to_shared(hs.buf)),
-                     "l"(A.verts), "r"(A.nvert * 16u), "r"(hs.bar)
-                     : "memory");
-      if (stB)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         (unsigned)__cvta_generic_to_shared(hs.buf + offB)),
-                     "l"(B.verts), "r"(B.nvert * 16u), "r"(hs.bar)
-                     : "memory");
-    }
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_HULL:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_HULL;\n"
-        "bra WAIT_HULL;\n"
-        "DONE_HULL:\n"
-        "}\n" ::"r"(hs.bar), "r"(hs.phase)
-        : "memory");
-    hs.phase ^= 1u;
-  }
-  if (stA) { A.verts = hs.buf; A.soff = hs.soff; }
-  if (stB) { B.verts = hs.buf + offB; B.soff = hs.soff + offB; }
-}
-
-__device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon, int& nnarrow, int& flags, HullStage& hs, int lane) {
+// Broadphase (runs in the smooth kernel): world positions of the collision geoms, then bounding spheres and
+// oriented bounding boxes over the compile-time pair list.  Passing pairs keep the reference's pair order:
+// slot s of env e holds the s-th passing pair (a.slot_pair) and becomes one work item of the narrowphase kernel.
+__device__ __forceinline__ void broadphase(const DevModel& m, const StepArgs& a, float* S, int env, int& flags, int lane) {
   const EnvLayout& o = m.L;
   float* gpos = S + o.gpos;
   _Pragma("unroll 1") for (int g = lane; g < m.ncgeom; g += 32) {
@@ -1321,8 +1277,7 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
     gpos[3 * g] = S[o.xpos + 3 * b] + t[0]; gpos[3 * g + 1] = S[o.xpos + 3 * b + 1] + t[1]; gpos[3 * g + 2] = S[o.xpos + 3 * b + 2] + t[2];
   }
   __syncwarp();
-  ncon = 0;
-  hs.resA = -1; hs.nA = 0;   // the Jacobian region was overwritten since the previous step
+  int npass = 0;
   for (int base = 0; base < m.npair; base += 32) {
     int p = base + lane;
     bool pass = false;
@@ -1401,43 +1356,23 @@ __device__ __forceinline__ void collision(const DevModel& m, float* S, int& ncon
       }
     }
     unsigned mask = __ballot_sync(FULL, pass);
-    nnarrow += __popc(mask);
-    long long tn0 = PROF_NOW(); (void)tn0;
-    while (mask) {
-      int bit = __ffs(mask) - 1;
-      mask &= mask - 1;
-      int pair = base + bit;
-      int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
-      Cvx A, B;
-      const int so = (int)(S + o.e_R - smem);   // narrowphase result record: the row arrays are not built yet
-      make_cvx(m, S, c1, A);
-      make_cvx(m, S, c2, B);
-      if (A.type != GEOM_PLANE) stage_pair(hs, A, B, lane);
-      narrow_pair(m, A, B, m.pair_margin[pair], m.multiccd ? 1e-3f * fminf(PKF(cg_rbound)[c1], PKF(cg_rbound)[c2]) : 0.f, so, lane);
-      const int ocount = __float_as_int(smem[so]);
-      for (int c = 0; c < ocount; c++) {
-        if (ncon >= m.maxcon) { flags |= 2; break; }
-        if (lane == 0) {
-          float* cr = S + o.con + ncon * CON_STRIDE;
-          const float* rec = smem + so + 4 + 8 * c;
-          float x[3] = {rec[0], rec[1], rec[2]}, y[3] = {0, 1, 0}, z[3];
-          if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
-          float d = dot3(x, y);
-          y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
-          normalize3(y);
-          cross3(z, x, y);
-          for (int k = 0; k < 3; k++) { cr[C_POS + k] = rec[4 + k]; cr[C_FRAME + k] = x[k]; cr[C_FRAME + 3 + k] = y[k]; cr[C_FRAME + 6 + k] = z[k]; }
-          cr[C_DIST] = rec[3]; cr[C_MU] = 0;
-          cr[C_DIM] = __int_as_float(m.pair_condim[pair]); cr[C_PAIR] = __int_as_float(pair); cr[C_EFC] = __int_as_float(-1);
-          cr[C_BODY1] = __int_as_float(PKI(cg_bodyid)[c1]); cr[C_BODY2] = __int_as_float(PKI(cg_bodyid)[c2]);
-          for (int k = 0; k < 5; k++) cr[C_FRICTION + k] = m.pair_friction[5 * pair + k];
-        }
-        ncon++;
+    int cnt = __popc(mask);
+    if (cnt) {
+      int slot = npass + __popc(mask & ((1u << lane) - 1));
+      int qbase = 0;
+      int room = max(0, min(cnt, a.maxslot - npass));
+      if (cnt > room) flags |= 2;
+      if (lane == 0 && room) qbase = atomicAdd(a.item_count, room);
+      qbase = __shfl_sync(FULL, qbase, 0);
+      if (pass && slot < a.maxslot) {
+        int item = env * a.maxslot + slot;
+        a.slot_pair[item] = p;
+        a.items[qbase + slot - npass] = item;
       }
-      __syncwarp();
+      npass += room;
     }
-    PROF_ADD(30, tn0);
   }
+  if (lane == 0) a.npass[env] = npass;
   __syncwarp();
 }
 
@@ -1535,7 +1470,6 @@ __device__ __forceinline__ void smooth_forces(const DevModel& m, float* S, int l
     if (k != 0 && PKI(jnt_type)[j] >= JNT_SLIDE) { int qa = PKI(jnt_qposadr)[j]; q -= k * (qpos[qa] - PKF(qpos_spring)[qa]); }
     for (int a = 0; a < m.nu; a++) q += PKF(act_moment)[a * nv + i] * actforce[a];
     qs[i] = q;
-    S[o.qacc_smooth + i] = q;
   }
   __syncwarp();
 }
@@ -1679,6 +1613,9 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
         J[(crow + r) * ldj + i] = (r < 3) ? dot3(ax, jp) : dot3(ax, jr);
       }
     }
+    // the row padding [nv, ldj) is read by the float4 operand loads of the Hessian build: it must be zero
+    // (0 x stale NaN bit patterns would poison the identity rows of the register tile)
+    if (lane < ldj - nv) for (int r = 0; r < dim; r++) J[(crow + r) * ldj + nv + lane] = 0.f;
     __syncwarp();
     if (lane < dim) {
       int r = lane, row = ns + crow + r;
@@ -1947,14 +1884,13 @@ __device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* 
   __syncwarp();
 }
 
-// ----------------------------------------------------------------------------- kernel
+// ----------------------------------------------------------------------------- kernels
+struct FwdInfo { int ncon, ns, nefc, iter, nnarrow; };
 __device__ __forceinline__ bool warp_bad(const float* x, int n, int lane) {
   bool bad = false;
   _Pragma("unroll 1") for (int i = lane; i < n; i += 32) bad |= !(fabsf(x[i]) < MAXVAL);
   return __any_sync(FULL, bad);
 }
-
-struct FwdInfo { int ncon, ns, nefc, iter, nnarrow; };
 
 // TMA bulk copy of the model pack into shared memory (one elected thread issues, all wait)
 __device__ __forceinline__ void load_pack(const uint32_t* src, int nwords) {
@@ -1989,147 +1925,233 @@ __device__ __forceinline__ void load_pack(const uint32_t* src, int nwords) {
       : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(256, 1) ss_physics_kernel(const DevModel m, const StepArgs a) {
+// ---- kernel 1: smooth dynamics + broadphase, one warp per env -------------------------------------------
+// Reads the state, writes the env's persistent block (a.pb), the broadphase result (a.npass, a.slot_pair, the
+// work-item queue a.items) and the pose / actuator observations.  Cost per env is uniform, so envs are
+// assigned statically; the CTA-wide stage barriers (a.sync_level & 1) keep the warps in the same code region.
+extern "C" __global__ void __launch_bounds__(512, 1) ss_smooth_kernel(const DevModel m, const StepArgs a) {
   const EnvLayout& o = m.L;
   load_pack(m.pack, m.pk.nwords);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* S = smem + m.pk.nwords + (size_t)warp * o.total;
-  // Work distribution: groups of `wpb` consecutive slots of the cost-sorted env order (heaviest
-  // first, api.cu:schedule_kernel) are handed out through an atomic counter, so the warps of a
-  // CTA own envs of similar cost (less waiting at the stage barriers) and light groups fill the
-  // tail.  Every warp of the CTA runs the same steps so that the CTA-wide barriers are uniform;
-  // the barriers keep the warps in the same code region, which is what makes the instruction
-  // cache work for this 400+ KB kernel (profiles/physics_r1.md).
-  __shared__ int s_group[8];
-  // barrier groups: the CTA's warps are split into groups of a.group_warps that synchronise among
-  // themselves only (named barriers 1..), fetch work independently and overlap each other's waits
-  int gw = a.group_warps > 0 ? min(a.group_warps, wpb) : wpb, grp = warp / gw, w0 = grp * gw, nwg = min(gw, wpb - w0);
-  int bar = (1 + grp) | ((nwg * 32) << 8);
-  __shared__ __align__(8) unsigned long long hull_bar[8];
-  HullStage hs;
-  hs.buf = reinterpret_cast<float4*>(S + o.J); hs.cap = (m.maxcrow * o.ldj) / 4; hs.soff = (int)((S + o.J) - smem) / 4; hs.phase = 0; hs.resA = -1; hs.nA = 0;
-  hs.bar = (unsigned)__cvta_generic_to_shared(&hull_bar[warp]);
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs.bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-#define STAGE_SYNC(level) do { if ((a.sync_level & 7) >= (level) && attempt == 0) group_sync(bar); } while (0)
-  for (;;) {
-    if (warp == w0 && lane == 0) s_group[grp] = atomicAdd(a.work_counter, nwg);
-    group_sync(bar);
-    int slot = s_group[grp] + (warp - w0);
-    group_sync(bar);
-    if (slot - (warp - w0) >= a.nenv) break;
-    bool active = slot < a.nenv;
-    int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
-    PROF_BEGIN();
-    int cost = 0;
-    if (a.sync_level & 96) {   // debug: scrub the env slice (32: zeros, 64: NaNs) to expose reads of stale shared memory
-      float fill = (a.sync_level & 64) ? __int_as_float(0x7fc00000) : 0.f;
-      _Pragma("unroll 1") for (int i = lane; i < o.total; i += 32) S[i] = fill;
-      __syncwarp();
-    }
+  const bool sync = a.sync_level & 1;
+  for (int base = blockIdx.x * wpb; base < a.nenv; base += gridDim.x * wpb) {
+    bool active = base + warp < a.nenv;
+    int env = a.order[active ? base + warp : a.nenv - 1];   // idle warps shadow another env and store nothing
     _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = a.qpos[(size_t)env * m.nq + i];
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = a.qvel[(size_t)env * m.nv + i]; S[o.warm + i] = a.warm[(size_t)env * m.nv + i]; }
     _Pragma("unroll 1") for (int i = lane; i < m.nu; i += 32) S[o.ctrl + i] = a.ctrl[(size_t)env * m.nu + i];
     __syncwarp();
     int flags = a.env_flags ? a.env_flags[env] : 0;
-    float time = a.time ? a.time[env] : 0.f;
-    int nsteps = a.forward_only ? 1 : a.nsteps;
-    for (int s = 0; s < nsteps; s++) {
-      FwdInfo fi = {0, 0, 0, 0, 0};
-      // mj_checkPos / mj_checkVel, then forward; mj_checkAcc re-runs forward once from the reset state
-      bool bad = active && (warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane));
-      for (int attempt = 0; attempt < 2; attempt++) {
-        if (bad) {
-          _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
-          _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
-          __syncwarp();
-          flags |= 1;
-        }
-        STAGE_SYNC(1);
-        PROF(16);
-        if (active) kinematics(m, S, lane);
-        PROF(17);
-        STAGE_SYNC(2);
-        if (active) crb_mass_matrix(m, S, lane);
-        PROF(18);
-        STAGE_SYNC(1);
-        PROF(19);
-        if (active) collision(m, S, fi.ncon, fi.nnarrow, flags, hs, lane);
-        PROF(20);
-        STAGE_SYNC(1);
-        PROF(21);
-        if (active) velocity_stage(m, S, lane);
-        PROF(22);
-        STAGE_SYNC(2);
-        if (active) smooth_forces(m, S, lane);
-        PROF(23);
-        STAGE_SYNC(2);
-        if (active) make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
-        PROF(24);
-        STAGE_SYNC(1);
-        // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
-        {
-        int ssync = (attempt == 0 && (a.sync_level & 8)) ? bar : 0;
-        if (active) copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
-        if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, active, ssync);
-        else if (active) { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
-        PROF(25);
-        fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, active, ssync);
-        PROF(26);
-        cost = a.cost_w * fi.iter + fi.nnarrow;   // last step's cost: the predictor for the next launch's schedule
-        if (active) _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
-        __syncwarp();
-        }
-        bad = active && warp_bad(S + o.qacc, m.nv, lane);
-        if (!bad) break;
-      }
-      if (a.sync_level & 7) group_sync(bar);
-      if (s == nsteps - 1 && active) {
-        // observations of the state the step started from (same convention as mjData after mj_step)
-        imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
-        if (a.xpos) for (int i = lane; i < m.nbody * 3; i += 32) a.xpos[(size_t)env * m.nbody * 3 + i] = S[o.xpos + i];
-        if (a.xquat) for (int i = lane; i < m.nbody * 4; i += 32) a.xquat[(size_t)env * m.nbody * 4 + i] = S[o.xquat + i];
-        if (a.act_length) for (int i = lane; i < m.nu; i += 32) a.act_length[(size_t)env * m.nu + i] = S[o.actlen + i];
-        if (a.act_velocity) for (int i = lane; i < m.nu; i += 32) a.act_velocity[(size_t)env * m.nu + i] = S[o.actvel + i];
-        if (a.qacc) for (int i = lane; i < m.nv; i += 32) a.qacc[(size_t)env * m.nv + i] = S[o.qacc + i];
-        if (a.ncon && lane == 0) a.ncon[env] = fi.ncon;
-        if (a.solver_iter && lane == 0) a.solver_iter[env] = fi.iter;
-        if (a.contact_geom || a.contact_dist || a.dbg_contact_pos || a.dbg_contact_normal)
-          _Pragma("unroll 1") for (int c = lane; c < m.maxcon; c += 32) {
-            const float* con = S + o.con + c * CON_STRIDE;
-            bool live = c < fi.ncon;
-            size_t k = (size_t)env * m.maxcon + c;
-            if (a.contact_geom) {
-              int pc = live ? PKI(pair_cg)[__float_as_int(con[C_PAIR])] : 0;
-              a.contact_geom[2 * k] = live ? PKI(cg_geomid)[pc & 0xffff] : -1;
-              a.contact_geom[2 * k + 1] = live ? PKI(cg_geomid)[pc >> 16] : -1;
-            }
-            if (a.contact_dist) a.contact_dist[k] = live ? con[C_DIST] : 0.f;
-            if (a.dbg_contact_pos) for (int t = 0; t < 3; t++) a.dbg_contact_pos[3 * k + t] = live ? con[C_POS + t] : 0.f;
-            if (a.dbg_contact_normal) for (int t = 0; t < 3; t++) a.dbg_contact_normal[3 * k + t] = live ? con[C_FRAME + t] : 0.f;
-          }
-        if (a.dbg_nefc && lane == 0) a.dbg_nefc[env] = fi.nefc;
-        if (a.dbg_M) for (int i = lane; i < m.nv * m.nv; i += 32) a.dbg_M[(size_t)env * m.nv * m.nv + i] = S[o.M + (i / m.nv) * o.ldm + (i % m.nv)];
-        if (a.dbg_qacc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qacc_smooth[(size_t)env * m.nv + i] = S[o.qacc_smooth + i];
-        if (a.dbg_qfrc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_smooth[(size_t)env * m.nv + i] = S[o.qfrc_smooth + i];
-        if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
-        __syncwarp();
-      }
-      PROF(27);
-      if (!a.forward_only) { integrate(m, S, lane, active, (a.sync_level & 8) ? bar : 0); time += m.timestep; }
-      PROF(28);
+    const int flags0 = flags;
+    // mj_checkPos / mj_checkVel: a bad state is replaced by qpos0 at rest
+    if (warp_bad(S + o.qpos, m.nq, lane) || warp_bad(S + o.qvel, m.nv, lane)) {
+      _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
+      _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; }
+      __syncwarp();
+      flags |= 1;
     }
-    if (!a.forward_only && active) {
-      _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
-      _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { a.qvel[(size_t)env * m.nv + i] = S[o.qvel + i]; a.warm[(size_t)env * m.nv + i] = S[o.warm + i]; }
-      if (a.time && lane == 0) a.time[env] = time;
+    if (sync) __syncthreads();
+    kinematics(m, S, lane);
+    if (sync) __syncthreads();
+    crb_mass_matrix(m, S, lane);
+    if (sync) __syncthreads();
+    if (active) broadphase(m, a, S, env, flags, lane);
+    if (sync) __syncthreads();
+    velocity_stage(m, S, lane);
+    if (sync) __syncthreads();
+    smooth_forces(m, S, lane);
+    if (active) {
+      float4* dst = reinterpret_cast<float4*>(a.pb + (size_t)env * a.pb_stride);
+      const float4* src = reinterpret_cast<const float4*>(S);
+      _Pragma("unroll 4") for (int i = lane; i < o.pb >> 2; i += 32) dst[i] = src[i];
+      if (a.xpos) for (int i = lane; i < m.nbody * 3; i += 32) a.xpos[(size_t)env * m.nbody * 3 + i] = S[o.xpos + i];
+      if (a.xquat) for (int i = lane; i < m.nbody * 4; i += 32) a.xquat[(size_t)env * m.nbody * 4 + i] = S[o.xquat + i];
+      if (a.act_length) for (int i = lane; i < m.nu; i += 32) a.act_length[(size_t)env * m.nu + i] = S[o.actlen + i];
+      if (a.act_velocity) for (int i = lane; i < m.nu; i += 32) a.act_velocity[(size_t)env * m.nu + i] = S[o.actvel + i];
+      if (a.env_flags && lane == 0 && flags != flags0) a.env_flags[env] = flags;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- kernel 2: narrowphase, one warp per (env, candidate pair) work item ---------------------------------
+// Work items come from the broadphase queue through an atomic counter, so the expensive queries (MPR on mesh
+// hulls, five of them per penetrating pair with multiccd) spread over all SMs instead of stalling the warps that
+// share a CTA with their env.  Hull vertices are read through L1 (this kernel uses almost no shared memory).
+extern "C" __global__ void __launch_bounds__(256, 2) ss_narrow_kernel(const DevModel m, const StepArgs a) {
+  load_pack(m.pack, m.pk.nwords);
+  const EnvLayout& o = m.L;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int so = m.pk.nwords + warp * NP_SMEM;
+  const int nitem = *a.item_count;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(a.item_next, 1);
+    it = __shfl_sync(FULL, it, 0);
+    if (it >= nitem) break;
+    int item = a.items[it], env = item / a.maxslot, pair = a.slot_pair[item];
+    const float* S = a.pb + (size_t)env * a.pb_stride;
+    int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
+    Cvx A, B;
+    make_cvx(m, S, c1, A);
+    make_cvx(m, S, c2, B);
+    narrow_pair(m, A, B, m.pair_margin[pair], m.multiccd ? 1e-3f * fminf(PKF(cg_rbound)[c1], PKF(cg_rbound)[c2]) : 0.f, so, lane);
+    float* r = a.rec + (size_t)item * NP_REC;
+    int n = 4 + 8 * __float_as_int(smem[so]);
+    for (int i = lane; i < n; i += 32) r[i] = smem[so + i];
+    __syncwarp();
+  }
+  (void)o;
+}
+
+// contacts of one env in the reference order (pair order, then the narrowphase's own order) from the records of
+// its broadphase slots: lane = slot for the counts (prefix sum), then each lane expands its slot's contacts
+__device__ __forceinline__ void gather_contacts(const DevModel& m, const StepArgs& a, float* S, int env, int& ncon, int& npass_out, int& flags, int lane) {
+  const EnvLayout& o = m.L;
+  int npass = a.npass[env];
+  npass_out = npass;
+  ncon = 0;
+  for (int base = 0; base < npass; base += 32) {
+    int slot = base + lane, cnt = 0, pair = 0;
+    const float* r = nullptr;
+    if (slot < npass) {
+      int item = env * a.maxslot + slot;
+      r = a.rec + (size_t)item * NP_REC;
+      cnt = __float_as_int(r[0]);
+      pair = a.slot_pair[item];
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    int start = ncon + incl - cnt;
+    if (cnt) {
+      int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
+      for (int c = 0; c < cnt; c++) {
+        int k = start + c;
+        if (k >= m.maxcon) { flags |= 2; break; }
+        float* cr = S + o.con + k * CON_STRIDE;
+        const float* rec = r + 4 + 8 * c;
+        float x[3] = {rec[0], rec[1], rec[2]}, y[3] = {0, 1, 0}, z[3];
+        if (x[1] > 0.5f || x[1] < -0.5f) { y[1] = 0; y[2] = 1; }
+        float d = dot3(x, y);
+        y[0] -= x[0] * d; y[1] -= x[1] * d; y[2] -= x[2] * d;
+        normalize3(y);
+        cross3(z, x, y);
+        for (int t = 0; t < 3; t++) { cr[C_POS + t] = rec[4 + t]; cr[C_FRAME + t] = x[t]; cr[C_FRAME + 3 + t] = y[t]; cr[C_FRAME + 6 + t] = z[t]; }
+        cr[C_DIST] = rec[3]; cr[C_MU] = 0;
+        cr[C_DIM] = __int_as_float(m.pair_condim[pair]); cr[C_PAIR] = __int_as_float(pair); cr[C_EFC] = __int_as_float(-1);
+        cr[C_BODY1] = __int_as_float(PKI(cg_bodyid)[c1]); cr[C_BODY2] = __int_as_float(PKI(cg_bodyid)[c2]);
+        for (int t = 0; t < 5; t++) cr[C_FRICTION + t] = m.pair_friction[5 * pair + t];
+      }
+    }
+    ncon += __shfl_sync(FULL, incl, 31);
+  }
+  flags |= __reduce_or_sync(FULL, (unsigned)flags);
+  if (ncon > m.maxcon) ncon = m.maxcon;
+  __syncwarp();
+}
+
+// ---- kernel 3: constraints, Newton solver, sensors, integration; one warp per env ------------------------
+// Work distribution: a.sync_level & 8 = lockstep mode: groups of `wpb` consecutive slots of the cost-sorted env
+// order (heaviest first, api.cu:schedule_kernel) are handed out through an atomic counter, the warps of a CTA
+// own envs of similar cost and meet at one barrier per Newton iteration (they then stream the long
+// straight-line factorisation through the instruction cache together).  Otherwise every warp fetches its
+// own env and runs free.
+extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevModel m, const StepArgs a) {
+  const EnvLayout& o = m.L;
+  load_pack(m.pack, m.pk.nwords);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* S = smem + m.pk.nwords + (size_t)warp * o.total;
+  __shared__ int s_group;
+  const bool lock = (a.sync_level & 8) != 0;
+  const int bar = lock ? (1 | ((wpb * 32) << 8)) : 0;
+  for (;;) {
+    int slot;
+    if (lock) {
+      if (threadIdx.x == 0) s_group = atomicAdd(a.work_counter, wpb);
+      __syncthreads();
+      slot = s_group + warp;
+      __syncthreads();
+      if (slot - warp >= a.nenv) break;
+    } else {
+      slot = 0;
+      if (lane == 0) slot = atomicAdd(a.work_counter, 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= a.nenv) break;
+    }
+    bool active = slot < a.nenv;
+    int env = a.order[active ? slot : a.nenv - 1];  // idle warps shadow another env read-only and store nothing
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.pb + (size_t)env * a.pb_stride);
+      float4* dst = reinterpret_cast<float4*>(S);
+      _Pragma("unroll 4") for (int i = lane; i < o.pb >> 2; i += 32) dst[i] = src[i];
+    }
+    if (a.sync_level & 96) {   // debug: scrub the env slice behind the persistent block (32: zeros, 64: NaNs) to expose reads of stale shared memory
+      float fill = (a.sync_level & 64) ? __int_as_float(0x7fc00000) : 0.f;
+      _Pragma("unroll 1") for (int i = o.pb + lane; i < o.total; i += 32) S[i] = fill;
+    }
+    __syncwarp();
+    int flags = a.env_flags ? a.env_flags[env] : 0;
+    float time = a.time ? a.time[env] : 0.f;
+    FwdInfo fi = {0, 0, 0, 0, 0};
+    gather_contacts(m, a, S, env, fi.ncon, fi.nnarrow, flags, lane);
+    make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
+    // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
+    _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.qacc_smooth + i] = S[o.qfrc_smooth + i];
+    copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
+    if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, true, bar);
+    else { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
+    fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, true, bar);
+    int cost = a.cost_w * fi.iter + fi.nnarrow;   // this step's cost: the predictor for the next launch's schedule
+    _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
+    __syncwarp();
+    // mj_checkAcc: a bad acceleration resets the env to qpos0 at rest (no integration in this step)
+    bool bad = warp_bad(S + o.qacc, m.nv, lane);
+    if (bad) {
+      _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) S[o.qpos + i] = PKF(qpos0)[i];
+      _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { S[o.qvel + i] = 0; S[o.warm + i] = 0; S[o.qacc + i] = 0; S[o.qfrc_con + i] = 0; S[o.qfrc_smooth + i] = 0; }
+      __syncwarp();
+      flags |= 1;
+    }
+    if (active) {
+      // observations of the state the step started from (same convention as mjData after mj_step)
+      if (!bad) imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
+      if (a.qacc) for (int i = lane; i < m.nv; i += 32) a.qacc[(size_t)env * m.nv + i] = S[o.qacc + i];
+      if (a.ncon && lane == 0) a.ncon[env] = fi.ncon;
+      if (a.solver_iter && lane == 0) a.solver_iter[env] = fi.iter;
+      if (a.contact_geom || a.contact_dist || a.dbg_contact_pos || a.dbg_contact_normal)
+        _Pragma("unroll 1") for (int c = lane; c < m.maxcon; c += 32) {
+          const float* con = S + o.con + c * CON_STRIDE;
+          bool live = c < fi.ncon;
+          size_t k = (size_t)env * m.maxcon + c;
+          if (a.contact_geom) {
+            int pc = live ? PKI(pair_cg)[__float_as_int(con[C_PAIR])] : 0;
+            a.contact_geom[2 * k] = live ? PKI(cg_geomid)[pc & 0xffff] : -1;
+            a.contact_geom[2 * k + 1] = live ? PKI(cg_geomid)[pc >> 16] : -1;
+          }
+          if (a.contact_dist) a.contact_dist[k] = live ? con[C_DIST] : 0.f;
+          if (a.dbg_contact_pos) for (int t = 0; t < 3; t++) a.dbg_contact_pos[3 * k + t] = live ? con[C_POS + t] : 0.f;
+          if (a.dbg_contact_normal) for (int t = 0; t < 3; t++) a.dbg_contact_normal[3 * k + t] = live ? con[C_FRAME + t] : 0.f;
+        }
+      if (a.dbg_nefc && lane == 0) a.dbg_nefc[env] = fi.nefc;
+      if (a.dbg_M) for (int i = lane; i < m.nv * m.nv; i += 32) a.dbg_M[(size_t)env * m.nv * m.nv + i] = S[o.M + (i / m.nv) * o.ldm + (i % m.nv)];
+      if (a.dbg_qacc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qacc_smooth[(size_t)env * m.nv + i] = S[o.qacc_smooth + i];
+      if (a.dbg_qfrc_smooth) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_smooth[(size_t)env * m.nv + i] = S[o.qfrc_smooth + i];
+      if (a.dbg_qfrc_constraint) for (int i = lane; i < m.nv; i += 32) a.dbg_qfrc_constraint[(size_t)env * m.nv + i] = S[o.qfrc_con + i];
+      __syncwarp();
+    }
+    if (!a.forward_only) {
+      if (!bad || lock) integrate(m, S, lane, !bad, bar);
+      time += m.timestep;
+      if (active) {
+        _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
+        _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) { a.qvel[(size_t)env * m.nv + i] = S[o.qvel + i]; a.warm[(size_t)env * m.nv + i] = S[o.warm + i]; }
+        if (a.time && lane == 0) a.time[env] = time;
+        if (lane == 0) a.cost[env] = cost;
+      }
     }
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
-    if (lane == 0 && active && !a.forward_only) a.cost[env] = cost;
-    PROF(29);
     __syncwarp();
   }
 }

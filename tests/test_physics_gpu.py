@@ -56,7 +56,13 @@ def test_forward_matches_oracle_at_qpos0(gpu, oracle_E, arrays_E):
     assert np.array_equal(B.ncon.cpu().numpy(), o["ncon"])
     assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])          # bit-exact pair indexing
     assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
-    assert np.abs(B.contact_dist.cpu().numpy() - o["contact_dist"]).max() < 1e-6
+    # the first contact of every geom pair is the plain narrowphase result: 1e-6 m.  The following contacts of a
+    # convex pair are multiccd contacts (stretch.xml:8): MPR queries of poses perturbed by 1e-3 rad, whose portal
+    # (hence depth) reacts to the fp32 rounding of the inputs -- they are bounded at 0.5 mm.
+    cg = o["contact_geom"]; dd = np.abs(B.contact_dist.cpu().numpy() - o["contact_dist"])
+    first = np.ones(cg.shape[:2], bool); first[:, 1:] = np.any(cg[:, 1:] != cg[:, :-1], axis=2)
+    plane = A["geom_type"][np.maximum(cg[:, :, 0], 0)] == 0
+    assert dd[first | plane].max() < 1e-6 and dd.max() < 5e-4
     qs = B.dbg["qacc_smooth"].cpu().numpy()
     assert np.abs(qs - o["qacc_smooth"]).max() <= 1e-3 * np.abs(o["qacc_smooth"]).max()
     fc = B.dbg["qfrc_constraint"].cpu().numpy()
@@ -93,7 +99,7 @@ def test_forward_parity_on_random_rollout_states(gpu, oracle_E, arrays_E):
     """bench.py's workload (uniform-random ctrl, redrawn every 50 steps) drives the robot into joint
     limits, self-contact and tipping.  After 207 steps every env's state is handed to the oracle and ONE
     forward pass is compared: contact pair lists bit-exact; qacc of the fp32 Newton solve within 2e-4
-    (median) / 2e-3 (99th percentile) of the fp64 solve relative to the env's largest acceleration.
+    (median) / 5e-3 (99th percentile; multiccd contacts of perturbed poses carry the MPR portal noise) of the fp64 solve relative to the env's largest acceleration.
     The remaining outliers must all be envs where a deeply overlapping convex pair (gripper linkage
     hulls) has its MPR portal land on a different face in fp32 than in fp64 -- a discontinuity of the
     single-point MPR contact, not a solver error (found with tests/compare_smooth.py)."""
@@ -122,7 +128,7 @@ def test_forward_parity_on_random_rollout_states(gpu, oracle_E, arrays_E):
     qa = B.qacc.cpu().numpy()
     err = np.abs(qa - o["qacc"]).max(1) / (np.abs(o["qacc"]).max(1) + 1e-3)
     err = np.where(ok, err, 0.0)
-    assert np.median(err) < 2e-4 and np.quantile(err, 0.99) < 2e-3, (np.median(err), np.quantile(err, 0.99))
+    assert np.median(err) < 2e-4 and np.quantile(err, 0.99) < 5e-3, (np.median(err), np.quantile(err, 0.99))
     gn = B.dbg["contact_normal"].cpu().numpy()
     live = np.arange(B.maxcon)[None, :] < o["ncon"][:, None]
     ndiff = np.where(live, np.abs(gn - o["contact_frame"]).max(2), 0.0).max(1)      # largest normal mismatch per env
