@@ -40,8 +40,19 @@ static inline int ss_blob_open(ss_blob* b, const void* buf, size_t n) {
   if (need > n) return -1;
   b->entries = (const ss_blob_entry*)(b->base + 16);
   b->tables = (const ss_blob_names*)(b->base + 16 + (size_t)b->narrays * sizeof(ss_blob_entry));
-  for (uint32_t i = 0; i < b->narrays; i++)
-    if (b->entries[i].offset + b->entries[i].nbytes > n) return -1;
+  for (uint32_t i = 0; i < b->narrays; i++) {
+    const ss_blob_entry* e = &b->entries[i];
+    if (e->dtype > 3 || e->ndim > 4 || e->offset > n || e->nbytes > n - e->offset) return -1;   /* no offset + nbytes overflow */
+  }
+  for (uint32_t t = 0; t < b->ntables; t++) {
+    const ss_blob_names* nt = &b->tables[t];
+    if (nt->offset > n || nt->nbytes > n - nt->offset) return -1;
+    /* every one of the `count` names must be NUL-terminated inside the table */
+    uint32_t seen = 0;
+    for (uint64_t k = 0; k < nt->nbytes && seen < nt->count; k++)
+      if (b->base[nt->offset + k] == 0) seen++;
+    if (seen < nt->count) return -1;
+  }
   return 0;
 }
 

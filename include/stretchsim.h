@@ -46,6 +46,8 @@ const char* ss_id2name(const ss_model*, int objtype, int id);
  * "actuator_ctrlrange", "opt_timestep", ... (replaces direct mjModel attribute reads,
  * stretch_mujoco/mujoco_server.py:213-222,284,381,574).  Returns bytes written or <0. */
 long ss_model_get(const ss_model*, const char* field, void* dst, size_t bytes);
+/* element type (0 = f64, 1 = i32, 2 = f32, 3 = u8), rank and shape of a named model array */
+int ss_model_field_info(const ss_model*, const char* field, int* dtype, int* ndim, uint64_t shape[4]);
 /* runtime-mutable fields: "qpos0" (start pose, mujoco_server.py:219-225), "cam_fovy"
  * (mujoco_server_camera_manager.py:197-208), "opt_iterations", "opt_tolerance". */
 int ss_model_set(ss_model*, const char* field, const void* src, size_t bytes);
@@ -121,6 +123,10 @@ int ss_batch_pull_status(ss_batch*, float* status_dev, ss_stream);
 #define SS_CMD_WIDTH 44
 int ss_batch_apply_commands(ss_batch*, float* command_dev, float* base_state_dev, ss_stream);
 
+/* nsteps x { ss_batch_apply_commands; ss_batch_step(1) }: the reference's cadence, where push_command and
+ * BaseController.update run after every mj_step (stretch_mujoco/mujoco_server.py:378-379,450-463). */
+int ss_batch_step_controlled(ss_batch*, int nsteps, float* command_dev, float* base_state_dev, ss_stream);
+
 /* ---- sensors ---------------------------------------------------------------------------- */
 /* 2-D spinning lidar (row S2/L1): evaluates every <rangefinder> of the model for each env from
  * the body frames of the last step; out[nenv, nrange] in sensor order, -1 on miss, clamped to
@@ -143,6 +149,11 @@ int ss_batch_render(ss_batch*, int cam_id, int W, int H, float fovy_deg, uint8_t
  * [nenv,W,H,3] / [nenv,W,H]), bgr != 0 = cv2.COLOR_RGB2BGR channel order. */
 int ss_batch_render_post(ss_batch*, int cam_id, int W, int H, float fovy_deg, uint8_t* rgb_dev, float* depth_dev,
                          float depth_limit, int env_begin, int env_count, int rot90, int bgr, ss_stream);
+
+/* utils.get_depth_color_map (stretch_mujoco/utils.py:363-373; `use_depth_color_map` of
+ * StatusStretchCameras.get_camera_data): depth [nimg, npix] -> JET colour map, BGR uint8 [nimg, npix, 3],
+ * normalised per image with its own min / max. */
+int ss_depth_colormap(const float* depth_dev, int nimg, int npix, uint8_t* bgr_dev, ss_stream);
 
 const char* ss_last_error(void);
 const char* ss_version(void);

@@ -101,10 +101,15 @@ static int build_layout(DevModel& m, int kernel) {
   int nv = m.nv, nb = m.nbody;
   o.ldm = nv <= 32 ? ((nv + 3) & ~3) : (nv | 1);   // n <= 32: float4 rows (register Cholesky path); else odd stride (scalar, conflict-free)
   o.ldj = (nv + 3) & ~3;   // 16-byte aligned rows (float4 operand loads in the Hessian build)
-  o.qpos = take(m.nq); o.qvel = take(nv); o.ctrl = take(m.nu); o.warm = take(nv);
-  o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.cdof = take(nv * 6); o.cdofdot = take(nv * 6); o.cvel = take(nb * 6);
+  // persistent block, part A (staged in shared memory by the solve kernel) ...
+  o.qpos = take(m.nq); o.qvel = take(nv); o.warm = take(nv);
+  o.cdof = take(nv * 6);
   o.M = take(nv * o.ldm);
-  o.qfrc_smooth = take(nv); o.actforce = take(m.nu); o.actlen = take(m.nu); o.actvel = take(m.nu);
+  o.qfrc_smooth = take(nv); o.actforce = take(m.nu);
+  o.pbA = off;
+  // ... and part B (read from global memory where needed: narrowphase poses, contact Jacobians' reference points, IMU)
+  o.ctrl = take(m.nu); o.actlen = take(m.nu); o.actvel = take(m.nu);
+  o.xpos = take(nb * 3); o.xquat = take(nb * 4); o.cdofdot = take(nv * 6); o.cvel = take(nb * 6);
   o.gpos = take(m.ncgeom * 3);
   o.pb = off;
   if (kernel == 1) {
@@ -112,15 +117,16 @@ static int build_layout(DevModel& m, int kernel) {
     o.cacc = take(nb * 10); o.cfrc = take(nb * 6);
     o.crb = o.cacc;                      // composite inertias (10/body) die before the RNE accelerations (6/body) are born
   } else {
+    off = o.pbA;                         // part B stays in global memory: its offsets are only valid against the global block
     o.qacc = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
     o.con = take(m.maxcon * CON_STRIDE);
     o.s_d1 = take(m.maxsimple); o.s_c1 = take(m.maxsimple); o.s_d2 = take(m.maxsimple); o.s_c2 = take(m.maxsimple);
-    o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxrow); o.e_info = take(m.maxrow);
-    o.J = take(m.maxcrow * o.ldj);
-    o.H = take(nv * o.ldm); o.tmpJ = take(6 * o.ldj);
+    o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxsimple); o.e_info = take(m.maxrow);   // friction loss: simple rows only
+    o.J = take(std::max(m.maxcrow * o.ldj, nb * 6));
+    o.cacc = o.J;                        // the IMU pass rebuilds body accelerations after the solve, when J is dead
+    o.H = take(nv * o.ldm); o.tmpJ = take((nv <= 32 ? 2 : 6) * o.ldj);   // register-tile path stages two vectors, the shared-memory path a cone block
     o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
     o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
-    o.cacc = take(nb * 6);
   }
   o.total = off;
   return off;
@@ -158,6 +164,16 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
   M->b = b;
   const int32_t* sz = ss_blob_i32(&b, "sizes");
   if (!sz) { delete M; return ss_fail("model blob has no 'sizes' array"); }
+  if (ss_blob_count(&b, "sizes") < 16) { delete M; return ss_fail("model blob: 'sizes' must hold 16 entries"); }
+  {
+    static const char* req_f64[] = {"opt_timestep", "opt_gravity", "opt_impratio", "opt_tolerance", "opt_ls_tolerance", "stat_meaninertia",
+                                    "qpos0", "body_pos", "body_quat", "geom_size", "pair_margin", "hull_vert"};
+    static const char* req_i32[] = {"opt_iterations", "opt_ls_iterations", "opt_cone", "body_parentid", "jnt_type", "dof_parentid",
+                                    "geom_type", "pair_geom1", "pair_geom2", "mesh_hulladr", "mesh_hullnum"};
+    for (const char* n : req_f64) if (!ss_blob_f64(&b, n)) { delete M; return ss_fail("model blob: missing or mistyped f64 array '%s'", n); }
+    for (const char* n : req_i32) if (!ss_blob_i32(&b, n)) { delete M; return ss_fail("model blob: missing or mistyped i32 array '%s'", n); }
+    if (ss_blob_count(&b, "opt_gravity") < 3) { delete M; return ss_fail("model blob: opt_gravity needs 3 entries"); }
+  }
   M->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete M; return ss_fail("cudaSetDevice(%d) failed", device); }
   DevModel& m = M->dm;
@@ -260,29 +276,23 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
   for (float x : pmargin) m.max_margin = std::max(m.max_margin, x);
   PackBuilder P;
   PackOffsets& k = m.pk;
-  k.body_parentid = P.addi(parent); k.body_rootidx = P.addi(rootidx); k.body_jntnum = P.addi(i32(b, "body_jntnum"));
-  k.body_jntadr = P.addi(i32(b, "body_jntadr")); k.body_dofnum = P.addi(dofnum); k.body_dofadr = P.addi(dofadr);
-  k.lvl_adr = P.addi(lvl_adr); k.lvl_body = P.addi(lvl_body); k.child_adr = P.addi(child_adr); k.child_list = P.addi(child_list);
+  // ---- part 1: tables the solve kernel needs (it stages only [0, nwords3) of the pack) ----
+  k.body_parentid = P.addi(parent); k.body_rootidx = P.addi(rootidx);
+  k.body_dofnum = P.addi(dofnum); k.body_dofadr = P.addi(dofadr);
+  k.lvl_adr = P.addi(lvl_adr); k.lvl_body = P.addi(lvl_body);
   k.root_list = P.addi(root_list); k.body_dofmask = P.addu(dofmask);
-  k.body_pos = P.addf(f32(b, "body_pos")); k.body_quat = P.addf(f32(b, "body_quat")); k.body_ipos = P.addf(f32(b, "body_ipos"));
-  k.body_iquat = P.addf(f32(b, "body_iquat")); k.body_mass = P.addf(f32(b, "body_mass")); k.body_inertia = P.addf(f32(b, "body_inertia"));
-  k.body_gravcomp = P.addf(gravcomp); k.body_invweight0 = P.addf(f32(b, "body_invweight0"));
-  k.jnt_type = P.addi(jnt_type); k.jnt_bodyid = P.addi(i32(b, "jnt_bodyid")); k.jnt_qposadr = P.addi(jnt_qposadr);
+  k.body_invweight0 = P.addf(f32(b, "body_invweight0"));
+  k.jnt_type = P.addi(jnt_type); k.jnt_qposadr = P.addi(jnt_qposadr);
   k.jnt_dofadr = P.addi(jnt_dofadr); k.limited_list = P.addi(limited_list);
-  k.jnt_pos = P.addf(f32(b, "jnt_pos")); k.jnt_axis = P.addf(f32(b, "jnt_axis")); k.jnt_stiffness = P.addf(f32(b, "jnt_stiffness"));
   k.jnt_range = P.addf(f32(b, "jnt_range")); k.jnt_margin = P.addf(f32(b, "jnt_margin")); k.jnt_solref = P.addf(f32(b, "jnt_solref"));
   k.jnt_solimp = P.addf(f32(b, "jnt_solimp"));
   M->qpos0_host = f32(b, "qpos0");
-  k.qpos0 = P.addf(M->qpos0_host); k.qpos_spring = P.addf(f32(b, "qpos_spring"));
-  k.dof_bodyid = P.addi(i32(b, "dof_bodyid")); k.dof_jntid = P.addi(dof_jnt); k.dof_parentid = P.addi(dof_parent);
-  k.dof_qposadr = P.addi(dof_qposadr); k.floss_list = P.addi(floss_list);
-  k.dof_armature = P.addf(f32(b, "dof_armature")); k.dof_damping = P.addf(f32(b, "dof_damping")); k.dof_frictionloss = P.addf(floss);
+  k.qpos0 = P.addf(M->qpos0_host);
+  k.dof_bodyid = P.addi(i32(b, "dof_bodyid")); k.floss_list = P.addi(floss_list);
+  k.dof_damping = P.addf(f32(b, "dof_damping")); k.dof_frictionloss = P.addf(floss);
   k.dof_invweight0 = P.addf(f32(b, "dof_invweight0")); k.dof_solref = P.addf(f32(b, "dof_solref")); k.dof_solimp = P.addf(f32(b, "dof_solimp"));
-  k.cg_geomid = P.addi(cg_geomid); k.cg_type = P.addi(cg_type); k.cg_bodyid = P.addi(cg_body); k.cg_dataid = P.addi(cg_data);
-  k.cg_size = P.addf(cg_size); k.cg_rbound = P.addf(cg_rb); k.cg_pos = P.addf(cg_pos); k.cg_quat = P.addf(cg_quat); k.cg_aabb = P.addf(cg_aabb);
-  k.pair_cg = P.addi(pair_cg);
-  k.mesh_hulladr = P.addi(i32(b, "mesh_hulladr")); k.mesh_hullnum = P.addi(i32(b, "mesh_hullnum"));
-  // only the sites that sensors of the physics kernel use (IMU); lidar sites live in the ray model
+  k.cg_geomid = P.addi(cg_geomid); k.cg_bodyid = P.addi(cg_body);
+  // only the sites that sensors of the physics kernels use (IMU); lidar sites live in the ray model
   {
     std::vector<int> sobj = i32(b, "sensor_objid"), sadr = i32(b, "sensor_adr"), sbody = i32(b, "site_bodyid");
     std::vector<float> spos = f32(b, "site_pos"), squat = f32(b, "site_quat");
@@ -301,10 +311,27 @@ extern "C" int ss_model_load_blob(const void* blob, size_t nbytes, int device, s
   }
   k.eq_obj1id = P.addi(i32(b, "eq_obj1id")); k.eq_obj2id = P.addi(i32(b, "eq_obj2id")); k.eq_active0 = P.addi(i32(b, "eq_active0"));
   k.eq_data = P.addf(f32(b, "eq_data")); k.eq_solref = P.addf(f32(b, "eq_solref")); k.eq_solimp = P.addf(f32(b, "eq_solimp"));
-  k.actuator_ctrllimited = P.addi(i32(b, "actuator_ctrllimited")); k.actuator_forcelimited = P.addi(i32(b, "actuator_forcelimited"));
-  k.actuator_gainprm = P.addf(f32(b, "actuator_gainprm")); k.actuator_biasprm = P.addf(f32(b, "actuator_biasprm"));
-  k.actuator_ctrlrange = P.addf(f32(b, "actuator_ctrlrange")); k.actuator_forcerange = P.addf(f32(b, "actuator_forcerange"));
+  k.actuator_forcelimited = P.addi(i32(b, "actuator_forcelimited"));
+  k.actuator_biasprm = P.addf(f32(b, "actuator_biasprm")); k.actuator_forcerange = P.addf(f32(b, "actuator_forcerange"));
   k.act_moment = P.addf(moment);
+  k.nwords3 = (int)P.w.size();
+  // ---- part 2: kinematics, dynamics and collision tables (smooth and narrowphase kernels) ----
+  k.body_jntnum = P.addi(i32(b, "body_jntnum")); k.body_jntadr = P.addi(i32(b, "body_jntadr"));
+  k.child_adr = P.addi(child_adr); k.child_list = P.addi(child_list);
+  k.body_pos = P.addf(f32(b, "body_pos")); k.body_quat = P.addf(f32(b, "body_quat")); k.body_ipos = P.addf(f32(b, "body_ipos"));
+  k.body_iquat = P.addf(f32(b, "body_iquat")); k.body_mass = P.addf(f32(b, "body_mass")); k.body_inertia = P.addf(f32(b, "body_inertia"));
+  k.body_gravcomp = P.addf(gravcomp);
+  k.jnt_bodyid = P.addi(i32(b, "jnt_bodyid"));
+  k.jnt_pos = P.addf(f32(b, "jnt_pos")); k.jnt_axis = P.addf(f32(b, "jnt_axis")); k.jnt_stiffness = P.addf(f32(b, "jnt_stiffness"));
+  k.qpos_spring = P.addf(f32(b, "qpos_spring"));
+  k.dof_jntid = P.addi(dof_jnt); k.dof_parentid = P.addi(dof_parent); k.dof_qposadr = P.addi(dof_qposadr);
+  k.dof_armature = P.addf(f32(b, "dof_armature"));
+  k.cg_type = P.addi(cg_type); k.cg_dataid = P.addi(cg_data);
+  k.cg_size = P.addf(cg_size); k.cg_rbound = P.addf(cg_rb); k.cg_pos = P.addf(cg_pos); k.cg_quat = P.addf(cg_quat); k.cg_aabb = P.addf(cg_aabb);
+  k.pair_cg = P.addi(pair_cg);
+  k.mesh_hulladr = P.addi(i32(b, "mesh_hulladr")); k.mesh_hullnum = P.addi(i32(b, "mesh_hullnum"));
+  k.actuator_ctrllimited = P.addi(i32(b, "actuator_ctrllimited"));
+  k.actuator_gainprm = P.addf(f32(b, "actuator_gainprm")); k.actuator_ctrlrange = P.addf(f32(b, "actuator_ctrlrange"));
   k.nwords = (int)P.w.size();
   M->pack_host = P.w;
   m.pack = upload(M, P.w);
@@ -361,6 +388,16 @@ extern "C" long ss_model_get(const ss_model* M, const char* field, void* dst, si
   return (long)e->nbytes;
 }
 
+extern "C" int ss_model_field_info(const ss_model* M, const char* field, int* dtype, int* ndim, uint64_t shape[4]) {
+  if (!M || !field) return ss_fail("ss_model_field_info: null argument");
+  const ss_blob_entry* e = ss_blob_find(&M->b, field);
+  if (!e) return ss_fail("ss_model_field_info: unknown field '%s'", field);
+  if (dtype) *dtype = (int)e->dtype;
+  if (ndim) *ndim = (int)e->ndim;
+  if (shape) for (int k = 0; k < 4; k++) shape[k] = e->shape[k];
+  return 0;
+}
+
 extern "C" int ss_model_set(ss_model* M, const char* field, const void* src, size_t bytes) {
   if (!M || !field || !src) return ss_fail("ss_model_set: null argument");
   cudaSetDevice(M->device);
@@ -386,7 +423,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   memset(&B->dbg, 0, sizeof(B->dbg));
   B->dm = M->dm;
   DevModel& m = B->dm;
-  m.maxcon = maxcon > 0 ? maxcon : 24;
+  m.maxcon = maxcon > 0 ? maxcon : 32;
   int nsimple = m.neq + m.nfloss + 2 * m.nlimited;
   m.maxsimple = nsimple;
   m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 96;
@@ -399,8 +436,9 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   int max_smem = 0, sms = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, M->device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
-  size_t pack_bytes = (size_t)m.pk.nwords * 4 + 2048;  // + static shared (mbarrier, compiler scratch) slack
-  int wpb = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env) : 0;
+  size_t pack_bytes = (size_t)m.pk.nwords * 4 + 1024;  // + static shared (mbarrier, compiler scratch) slack
+  size_t pack_bytes3 = (size_t)m.pk.nwords3 * 4 + 1024;
+  int wpb = max_smem > (int)pack_bytes3 ? (int)((max_smem - pack_bytes3) / B->smem_per_env) : 0;
   int wpb1 = max_smem > (int)pack_bytes ? (int)((max_smem - pack_bytes) / B->smem_per_env1) : 0;
   if (wpb < 1 || wpb1 < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
   wpb = std::min(wpb, 8);     // ss_solve_kernel: __launch_bounds__(256, 1), up to 255 registers per thread
@@ -412,6 +450,9 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   B->group_warps = 0;
   B->pack_bytes = (size_t)m.pk.nwords * 4;
   B->warps_per_block = wpb; B->warps_per_block1 = wpb1;
+  if (getenv("SS_VERBOSE"))
+    fprintf(stderr, "[stretchsim] pack %zu B (solve kernel: %d B), smooth kernel %zu B/env x %d warps, solve kernel %zu B/env x %d warps (persistent block %d floats, part A %d), shared memory limit %d B\n",
+            B->pack_bytes, m.pk.nwords3 * 4, B->smem_per_env1, wpb1, B->smem_per_env, wpb, m.L.pb, m.L.pbA, max_smem);
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
   B->grid1 = std::min((nenv + wpb1 - 1) / wpb1, sms);
   B->grid2 = 2 * sms;
@@ -431,8 +472,6 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
     ss_batch_free(B);
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  B->steps_per_launch = 1;   // measured (1 set): 50 -> 56.0, 10 -> 54.7, 5 -> 53.9, 2 -> 53.2, 1 -> 53.6 ms per 50 steps x 4096 envs; (2 sets): 2 -> 48.9, 1 -> 47.9
-  if (const char* e = getenv("SS_CHUNK")) B->steps_per_launch = std::max(1, atoi(e));
   B->nosort = getenv("SS_NOSORT") != nullptr;
   // schedule key: bucket = min(255, cost_scale * cost), cost = cost_w x Newton iterations + narrowphase queries
   // (47.3 ms per 50 steps for 16 / x1 against 47.9 ms for 8 / x4)
@@ -498,7 +537,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   a.pb = B->pb; a.pb_stride = B->pb_stride; a.maxslot = B->maxslot; a.npass = B->npass; a.slot_pair = B->slot_pair; a.rec = B->rec;
   // dynamic shared memory is per-function state shared by all batches of the process: set it before every
   // launch chain (a batch created later with a smaller footprint must not lower it for this one)
-  const size_t smem1 = B->pack_bytes + B->warps_per_block1 * B->smem_per_env1, smem3 = B->pack_bytes + B->warps_per_block * B->smem_per_env;
+  const size_t smem1 = B->pack_bytes + B->warps_per_block1 * B->smem_per_env1, smem3 = (size_t)B->dm.pk.nwords3 * 4 + B->warps_per_block * B->smem_per_env;
   const size_t smem2 = B->pack_bytes + (NARROW_THREADS / 32) * NP_SMEM * sizeof(float);
   CUDA_OK(cudaFuncSetAttribute(ss_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   CUDA_OK(cudaFuncSetAttribute(ss_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

@@ -23,6 +23,8 @@ struct ss_model {
   std::vector<void*> dev_allocs;
 };
 
+struct StatusIds { int act[10]; int base_body; };  // lift, arm, head_pan, head_tilt, wrist_yaw, wrist_pitch, wrist_roll, gripper, left_wheel, right_wheel
+
 #define SS_MAXSETS 4
 struct ss_batch {
   const ss_model* model;
@@ -37,13 +39,14 @@ struct ss_batch {
   float *pb = nullptr, *rec = nullptr;
   int32_t *npass = nullptr, *slot_pair = nullptr, *items = nullptr, *counters = nullptr;   // counters: 4 ints per env set
   long launches;
-  int steps_per_launch = 1;   // long rollouts are cut into launches of this many steps, re-sorted in between
   bool nosort = false;
   int cost_w = 16, cost_scale = 1;
   int nsets = 1;               // env sets with their own launch chains on side streams (tail overlap)
   cudaStream_t side[SS_MAXSETS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[SS_MAXSETS] = {};
   int32_t *order = nullptr, *cost = nullptr, *work_counter = nullptr;  // cost-sorted env schedule (api.cu)
+  StatusIds ids = {};
+  bool ids_valid = false;
   float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
 };
 

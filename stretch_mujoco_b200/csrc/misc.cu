@@ -49,7 +49,6 @@ extern "C" int ss_batch_reset(ss_batch* B, const int32_t* mask, int key_id, ss_s
   return 0;
 }
 
-struct StatusIds { int act[10]; int base_body; };  // lift, arm, head_pan, head_tilt, wrist_yaw, wrist_pitch, wrist_roll, gripper, left_wheel, right_wheel
 
 __global__ void status_kernel(int nenv, int nu, int nbody, StatusIds ids, const float* time, const float* len,
                               const float* vel, const float* xpos, const float* xquat, float* out) {
@@ -73,12 +72,18 @@ __global__ void status_kernel(int nenv, int nu, int nbody, StatusIds ids, const 
   s[22] = 0; s[23] = 0;
 }
 
-static int lookup_ids(const ss_batch* B, StatusIds* ids) {
-  static const char* names[10] = {"lift", "arm", "head_pan", "head_tilt", "wrist_yaw", "wrist_pitch", "wrist_roll",
-                                  "gripper", "left_wheel_vel", "right_wheel_vel"};
-  for (int k = 0; k < 10; k++) ids->act[k] = ss_name2id(B->model, SS_OBJ_ACTUATOR, names[k]);
-  ids->base_body = ss_name2id(B->model, SS_OBJ_BODY, "base_link");
-  if (ids->base_body < 0) return ss_fail("model has no body named base_link");
+// actuator / body ids of the status and command rows: looked up by name once per batch (the reference does the
+// same named lookups on every call, stretch_mujoco/mujoco_server.py:475-504)
+static int lookup_ids(ss_batch* B, StatusIds* ids) {
+  if (!B->ids_valid) {
+    static const char* names[10] = {"lift", "arm", "head_pan", "head_tilt", "wrist_yaw", "wrist_pitch", "wrist_roll",
+                                    "gripper", "left_wheel_vel", "right_wheel_vel"};
+    for (int k = 0; k < 10; k++) B->ids.act[k] = ss_name2id(B->model, SS_OBJ_ACTUATOR, names[k]);
+    B->ids.base_body = ss_name2id(B->model, SS_OBJ_BODY, "base_link");
+    if (B->ids.base_body < 0) return ss_fail("model has no body named base_link");
+    B->ids_valid = true;
+  }
+  *ids = B->ids;
   return 0;
 }
 
@@ -170,5 +175,16 @@ extern "C" int ss_batch_apply_commands(ss_batch* B, float* command_dev, float* b
                                                                            B->bufs.ctrl);
   B->launches++;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// The reference's control cadence: push_command + BaseController.update run after EVERY mj_step
+// (stretch_mujoco/mujoco_server.py:378-379,450-463), so the stop test of a base move_by is evaluated per step.
+extern "C" int ss_batch_step_controlled(ss_batch* B, int nsteps, float* command_dev, float* base_state_dev, ss_stream stream) {
+  if (!B || nsteps <= 0) return ss_fail("ss_batch_step_controlled: bad argument");
+  for (int k = 0; k < nsteps; k++) {
+    if (ss_batch_apply_commands(B, command_dev, base_state_dev, stream) != 0) return -1;
+    if (ss_batch_step(B, 1, stream) != 0) return -1;
+  }
   return 0;
 }

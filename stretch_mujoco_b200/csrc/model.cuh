@@ -24,11 +24,16 @@ enum { ST_SATISFIED = 0, ST_QUADRATIC, ST_LINEARNEG, ST_LINEARPOS, ST_CONE };
 // [0, pb): the fields that travel from the smooth kernel to the narrowphase and solve kernels through
 // global memory (one contiguous float4 copy per env).
 struct EnvLayout {
-  // persistent block
-  int qpos, qvel, ctrl, warm;
-  int xpos, xquat, cdof, cdofdot, cvel;
+  // persistent block, part A [0, pbA): staged in shared memory by the solve kernel
+  int qpos, qvel, warm;
+  int cdof;
   int M, ldm;                                    // dense nv x nv joint-space inertia, row stride ldm
-  int qfrc_smooth, actforce, actlen, actvel;
+  int qfrc_smooth, actforce;
+  int pbA;
+  // part B [pbA, pb): the solve kernel reads it from the global block (Jacobian reference points, IMU), the
+  // narrowphase kernel too (poses)
+  int ctrl, actlen, actvel;
+  int xpos, xquat, cdofdot, cvel;
   int gpos;                                      // world positions of the collision geoms
   int pb;                                        // size of the persistent block (multiple of 4)
   // smooth kernel only
@@ -72,7 +77,8 @@ struct PackOffsets {
   int eq_obj1id, eq_obj2id, eq_active0, eq_data, eq_solref, eq_solimp;
   int actuator_ctrllimited, actuator_forcelimited, actuator_gainprm, actuator_biasprm, actuator_ctrlrange,
       actuator_forcerange, act_moment;
-  int nwords;  // pack size in 32-bit words (multiple of 4)
+  int nwords;   // pack size in 32-bit words (multiple of 4)
+  int nwords3;  // leading part of the pack that the solve kernel stages (tables of the later part are not used there)
 };
 
 struct DevModel {

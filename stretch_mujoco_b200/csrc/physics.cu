@@ -28,21 +28,10 @@
 #define MAXIMP 0.9999f
 
 extern __shared__ __align__(16) float smem[];
-// Optional cycle accounting per stage (make PROFILE=1; tests/prof_solver.py reads it through ss_debug_prof)
-#ifdef SS_PROFILE
-__device__ unsigned long long g_prof[32];
-#define PROF_BEGIN() long long tprof = clock64()
-#define PROF(k) do { long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[k], (unsigned long long)(t_ - tprof)); tprof = t_; } while (0)
-#define PROF_ADD(k, t0) do { if (lane == 0) atomicAdd(&g_prof[k], (unsigned long long)(clock64() - (t0))); } while (0)
-#define PROF_NOW() clock64()
-#else
-#define PROF_BEGIN() do { } while (0)
-#define PROF(k) do { } while (0)
-#define PROF_ADD(k, t0) do { } while (0)
-#define PROF_NOW() 0
-#endif  // [model pack | env slice 0 | env slice 1 | ...]
+// [model pack | env slice 0 | env slice 1 | ...]
 #define PKF(name) (smem + m.pk.name)
 #define PKI(name) (reinterpret_cast<const int*>(smem) + m.pk.name)
+#define GPI(name) (reinterpret_cast<const int*>(m.pack) + m.pk.name)   // the same table in global memory
 
 // ----------------------------------------------------------------------------- small math
 __device__ __forceinline__ float warp_sum(float v) {
@@ -542,9 +531,7 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
     }
   }
   }
-  PROF_BEGIN();
   bool any = sync ? group_sync_or(sync, alive) : alive;
-  PROF(work ? 5 : 6);
   if (work) chol_solve_rows<NT>(h, H, nv, ld, xs, lane);
   return any;
 }
@@ -1507,8 +1494,8 @@ __device__ __noinline__ void row_params(float timestep, const float* solref, con
 }
 
 // Build constraint rows in the reference order: equality, friction loss, limits, contacts.
-__device__ __forceinline__ void make_constraints(const DevModel& m, float* S, int& ncon, int& ns_out, int& nefc_out, int& flags,
-                                                 int lane) {
+__device__ __forceinline__ void make_constraints(const DevModel& m, float* S, const float* __restrict__ G, int& ncon, int& ns_out,
+                                                 int& nefc_out, int& flags, int lane) {
   const EnvLayout& o = m.L;
   const float *qpos = S + o.qpos, *qvel = S + o.qvel;
   float *sc1 = S + o.s_c1, *sc2 = S + o.s_c2, *eR = S + o.e_R, *eD = S + o.e_D, *earef = S + o.e_aref, *efl = S + o.e_floss;
@@ -1589,7 +1576,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
   ns_out = ns;
   // contacts: dense Jacobian rows, lane = dof
   float* J = S + o.J;
-  const float *cdof = S + o.cdof, *xpos = S + o.xpos;
+  const float *cdof = S + o.cdof, *xpos = G + o.xpos;   // G: the env's global block (part B)
   int crow = 0, nv = m.nv, ldj = o.ldj;
   for (int c = 0; c < ncon; c++) {
     float* con = S + o.con + c * CON_STRIDE;
@@ -1628,7 +1615,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, in
       const float *solref = m.pair_solref + 2 * pair, *solimp = m.pair_solimp + 5 * pair;
       float inclmargin = m.pair_margin[pair] - m.pair_gap[pair];
       row_params(m.timestep, solref, solimp, r == 0 ? con[C_DIST] : 0.f, r == 0 ? inclmargin : 0.f, diag, vel, &R, &aref);
-      eR[row] = R; earef[row] = aref; efl[row] = 0;
+      eR[row] = R; earef[row] = aref;
       einfo[row] = ((dim == 1) ? CNSTR_CONTACT_FRICTIONLESS : CNSTR_CONTACT_ELLIPTIC) | (c << 8);
     }
     __syncwarp();
@@ -1699,7 +1686,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
   }
   }
   int iter = 0;
-  PROF_BEGIN();
   while (true) {
     if (!sync && done) break;
     if (!done) {
@@ -1711,7 +1697,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       if (iter >= m.iterations) done = true;
       else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
     }
-    PROF(done ? 7 : 0);
     if (nv <= 32) {
       // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
       // every warp whether any warp of the CTA is still iterating
@@ -1720,7 +1705,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       if (sync && !group_sync_or(sync, !done)) break;
       if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
     }
-    PROF(done ? 7 : 1);
     if (done) continue;
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
@@ -1732,7 +1716,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     float q1 = 0, q2 = 0;
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { q1 += search[i] * (Ma[i] - qs[i]); q2 += search[i] * mv[i]; }
     q1 = warp_sum(q1); q2 = warp_sum(q2);
-    PROF(2);
     // exact line search: safeguarded Newton on the monotone derivative p'(a)
     float gtol = m.tolerance * m.ls_tolerance * sqrtf(ss) / scale;
     // p'(0) = grad . search = gs and p''(0) = search^T H search = -gs, because search solves H search = -grad
@@ -1755,7 +1738,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       }
       a = an;
     }
-    PROF(3);
     if (!(a > 0)) { done = true; continue; }
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { qacc[i] += a * search[i]; Ma[i] += a * mv[i]; }
     _Pragma("unroll 1") for (int r = lane; r < nefc; r += 32) jar[r] += a * jv[r];
@@ -1768,7 +1750,6 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       cost += warp_sum(gsum);
     }
     iter++;
-    PROF(4);
     // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
     if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
       mul_JT(R, qfc, force, lane);
@@ -1835,10 +1816,10 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane,
 
 // ----------------------------------------------------------------------------- S4/S8: gyro + accelerometer
 // (runs after the solver: region X is free again, cacc is rebuilt there with qacc included)
-__device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* sensordata_env, int lane) {
+__device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, const float* __restrict__ G, float* sensordata_env, int lane) {
   if (sensordata_env == nullptr) return;
   const EnvLayout& o = m.L;
-  const float *cdof = S + o.cdof, *cdofdot = S + o.cdofdot, *qvel = S + o.qvel, *qacc = S + o.qacc;
+  const float *cdof = S + o.cdof, *cdofdot = G + o.cdofdot, *qvel = S + o.qvel, *qacc = S + o.qacc;   // G: the env's global block (part B)
   float* cacc = S + o.cacc;
   if (lane < 6) cacc[lane] = (lane < 3) ? 0.f : -m.gravity[lane - 3];
   __syncwarp();
@@ -1861,13 +1842,13 @@ __device__ __forceinline__ void imu_sensors(const DevModel& m, float* S, float* 
     if (type == SENS_RANGE) continue;
     int site = PKI(sensor_objid)[s], adr = PKI(sensor_adr)[s], b = PKI(site_bodyid)[site];
     float q[4], R[9], Rb[9], p[3], t[3];
-    quat_mul(q, S + o.xquat + 4 * b, PKF(site_quat) + 4 * site);
+    quat_mul(q, G + o.xquat + 4 * b, PKF(site_quat) + 4 * site);
     quat_normalize(q);
     quat2mat(R, q);
-    quat2mat(Rb, S + o.xquat + 4 * b);
+    quat2mat(Rb, G + o.xquat + 4 * b);
     mat_vec(t, Rb, PKF(site_pos) + 3 * site);
-    p[0] = S[o.xpos + 3 * b] + t[0]; p[1] = S[o.xpos + 3 * b + 1] + t[1]; p[2] = S[o.xpos + 3 * b + 2] + t[2];
-    const float *cv = S + o.cvel + 6 * b, *ca = cacc + 6 * b, *ref = S + o.xpos + 3 * PKI(root_list)[PKI(body_rootidx)[b]];
+    p[0] = G[o.xpos + 3 * b] + t[0]; p[1] = G[o.xpos + 3 * b + 1] + t[1]; p[2] = G[o.xpos + 3 * b + 2] + t[2];
+    const float *cv = G + o.cvel + 6 * b, *ca = cacc + 6 * b, *ref = G + o.xpos + 3 * PKI(root_list)[PKI(body_rootidx)[b]];
     float out[3];
     if (type == SENS_GYRO) {
       matT_vec(out, R, cv);
@@ -2026,7 +2007,7 @@ __device__ __forceinline__ void gather_contacts(const DevModel& m, const StepArg
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
     int start = ncon + incl - cnt;
     if (cnt) {
-      int pc = PKI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
+      int pc = GPI(pair_cg)[pair], c1 = pc & 0xffff, c2 = pc >> 16;
       for (int c = 0; c < cnt; c++) {
         int k = start + c;
         if (k >= m.maxcon) { flags |= 2; break; }
@@ -2060,9 +2041,9 @@ __device__ __forceinline__ void gather_contacts(const DevModel& m, const StepArg
 // own env and runs free.
 extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevModel m, const StepArgs a) {
   const EnvLayout& o = m.L;
-  load_pack(m.pack, m.pk.nwords);
+  load_pack(m.pack, m.pk.nwords3);   // part 1 of the pack only; pair_cg (part 2) is read from global memory (GPI)
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  float* S = smem + m.pk.nwords + (size_t)warp * o.total;
+  float* S = smem + m.pk.nwords3 + (size_t)warp * o.total;
   __shared__ int s_group;
   const bool lock = (a.sync_level & 8) != 0;
   const int bar = lock ? (1 | ((wpb * 32) << 8)) : 0;
@@ -2085,18 +2066,19 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
     {
       const float4* src = reinterpret_cast<const float4*>(a.pb + (size_t)env * a.pb_stride);
       float4* dst = reinterpret_cast<float4*>(S);
-      _Pragma("unroll 4") for (int i = lane; i < o.pb >> 2; i += 32) dst[i] = src[i];
+      _Pragma("unroll 4") for (int i = lane; i < o.pbA >> 2; i += 32) dst[i] = src[i];
     }
     if (a.sync_level & 96) {   // debug: scrub the env slice behind the persistent block (32: zeros, 64: NaNs) to expose reads of stale shared memory
       float fill = (a.sync_level & 64) ? __int_as_float(0x7fc00000) : 0.f;
-      _Pragma("unroll 1") for (int i = o.pb + lane; i < o.total; i += 32) S[i] = fill;
+      _Pragma("unroll 1") for (int i = o.pbA + lane; i < o.total; i += 32) S[i] = fill;
     }
     __syncwarp();
     int flags = a.env_flags ? a.env_flags[env] : 0;
     float time = a.time ? a.time[env] : 0.f;
     FwdInfo fi = {0, 0, 0, 0, 0};
     gather_contacts(m, a, S, env, fi.ncon, fi.nnarrow, flags, lane);
-    make_constraints(m, S, fi.ncon, fi.ns, fi.nefc, flags, lane);
+    const float* G = a.pb + (size_t)env * a.pb_stride;
+    make_constraints(m, S, G, fi.ncon, fi.ns, fi.nefc, flags, lane);
     // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.qacc_smooth + i] = S[o.qfrc_smooth + i];
     copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
@@ -2116,7 +2098,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
     }
     if (active) {
       // observations of the state the step started from (same convention as mjData after mj_step)
-      if (!bad) imu_sensors(m, S, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
+      if (!bad) imu_sensors(m, S, G, a.sensordata ? a.sensordata + (size_t)env * m.nsensordata : nullptr, lane);
       if (a.qacc) for (int i = lane; i < m.nv; i += 32) a.qacc[(size_t)env * m.nv + i] = S[o.qacc + i];
       if (a.ncon && lane == 0) a.ncon[env] = fi.ncon;
       if (a.solver_iter && lane == 0) a.solver_iter[env] = fi.iter;
@@ -2126,7 +2108,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
           bool live = c < fi.ncon;
           size_t k = (size_t)env * m.maxcon + c;
           if (a.contact_geom) {
-            int pc = live ? PKI(pair_cg)[__float_as_int(con[C_PAIR])] : 0;
+            int pc = live ? GPI(pair_cg)[__float_as_int(con[C_PAIR])] : 0;
             a.contact_geom[2 * k] = live ? PKI(cg_geomid)[pc & 0xffff] : -1;
             a.contact_geom[2 * k + 1] = live ? PKI(cg_geomid)[pc >> 16] : -1;
           }
@@ -2154,17 +2136,4 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
     __syncwarp();
   }
-}
-
-// cycle counters of the profiling build (32 x u64); returns -1 when the library was built without PROFILE=1
-extern "C" int ss_debug_prof(unsigned long long* out32, int reset) {
-#ifdef SS_PROFILE
-  unsigned long long z[32] = {0};
-  if (out32) cudaMemcpyFromSymbol(out32, g_prof, sizeof(z));
-  if (reset) cudaMemcpyToSymbol(g_prof, z, sizeof(z));
-  return 0;
-#else
-  (void)out32; (void)reset;
-  return -1;
-#endif
 }

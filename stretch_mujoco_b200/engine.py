@@ -20,10 +20,12 @@ STATUS_WIDTH = 24
 CMD_WIDTH = 44
 
 EXPORTS = [
-    "ss_model_load_blob", "ss_model_free", "ss_model_dims", "ss_name2id", "ss_id2name", "ss_model_get", "ss_model_set",
-    "ss_batch_create", "ss_batch_free", "ss_batch_reset", "ss_batch_step", "ss_batch_forward", "ss_batch_launch_count",
-    "ss_batch_set_debug", "ss_batch_pull_status", "ss_batch_apply_commands", "ss_batch_lidar",
-    "ss_model_num_rangefinders", "ss_batch_rays", "ss_batch_render", "ss_batch_render_post", "ss_last_error", "ss_version",
+    "ss_model_load_blob", "ss_model_free", "ss_model_dims", "ss_name2id", "ss_id2name", "ss_model_get", "ss_model_field_info",
+    "ss_model_set", "ss_batch_create", "ss_batch_free", "ss_batch_reset", "ss_batch_step", "ss_batch_forward",
+    "ss_batch_launch_count", "ss_batch_set_debug", "ss_batch_pull_status", "ss_batch_apply_commands",
+    "ss_batch_step_controlled", "ss_batch_lidar",
+    "ss_model_num_rangefinders", "ss_batch_rays", "ss_batch_render", "ss_batch_render_post", "ss_depth_colormap",
+    "ss_last_error", "ss_version",
 ]
 
 
@@ -65,6 +67,8 @@ def lib():
         L.ss_model_get.restype = C.c_long
         L.ss_model_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
         L.ss_model_set.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.ss_model_field_info.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+        L.ss_batch_step_controlled.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ss_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Buffers), C.POINTER(C.c_void_p)]
         L.ss_batch_free.argtypes = [C.c_void_p]
         L.ss_batch_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -83,8 +87,20 @@ def lib():
                                       C.c_int, C.c_int, C.c_void_p]
         L.ss_batch_render_post.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ss_depth_colormap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def depth_colormap(depth):
+    """JET colour map of depth images [n, H, W] (device tensor) -> BGR uint8 [n, H, W, 3], normalised per image
+    (utils.get_depth_color_map, stretch_mujoco/utils.py:363-373)."""
+    import torch
+    depth = depth.contiguous()
+    n = depth.shape[0]
+    out = torch.empty(*depth.shape, 3, dtype=torch.uint8, device=depth.device)
+    _check(lib().ss_depth_colormap(C.c_void_p(depth.data_ptr()), n, depth[0].numel(), C.c_void_p(out.data_ptr()), _stream()))
+    return out
 
 
 class StretchSimError(RuntimeError):
@@ -134,15 +150,18 @@ class DeviceModel:
         return r.decode() if r is not None else None
 
     def get(self, field: str) -> np.ndarray:
+        """Host copy of a named model array with the dtype and shape recorded in the model blob."""
+        dt, nd, shape = C.c_int(), C.c_int(), (C.c_uint64 * 4)()
+        _check(lib().ss_model_field_info(self._h, field.encode(), C.byref(dt), C.byref(nd), shape))
         n = _check(lib().ss_model_get(self._h, field.encode(), None, 0))
         buf = np.zeros(n, np.uint8)
-        _check(lib().ss_model_get(self._h, field.encode(), buf.ctypes.data_as(C.c_void_p), n))
-        if field.split("_")[-1] in ("type", "id", "adr", "num", "limited", "sizes", "bodyid", "parentid") or field in (
-                "sizes", "opt_iterations", "opt_ls_iterations", "opt_cone", "opt_solver", "opt_multiccd",
-                "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "geom_group", "geom_matid", "geom_dataid", "pair_geom1",
-                "pair_geom2", "pair_condim", "eq_active0", "exclude_signature"):
-            return buf.view(np.int32).copy()
-        return buf.view(np.float64).copy()
+        if n:
+            _check(lib().ss_model_get(self._h, field.encode(), buf.ctypes.data_as(C.c_void_p), n))
+        dtype = (np.float64, np.int32, np.float32, np.uint8)[dt.value]
+        arr = buf.view(dtype).copy()
+        if field == "qpos0":        # reflects ss_model_set; always fp64 [nq]
+            return arr
+        return arr.reshape([int(shape[k]) for k in range(nd.value)])
 
     def set(self, field: str, value) -> None:
         if field == "opt_iterations":
@@ -155,7 +174,7 @@ class DeviceModel:
 class Batch:
     """`nenv` independent envs on one GPU; all arrays are torch CUDA tensors, env-major."""
 
-    def __init__(self, model: DeviceModel, nenv: int, maxcon: int = 24, maxefc: int = 0, debug: bool = False):
+    def __init__(self, model: DeviceModel, nenv: int, maxcon: int = 32, maxefc: int = 0, debug: bool = False):
         import torch
         self.model, self.nenv, self.maxcon = model, nenv, maxcon
         dev = torch.device("cuda", model.device)
@@ -206,6 +225,11 @@ class Batch:
 
     def forward(self):
         _check(lib().ss_batch_forward(self._h, _stream()))
+
+    def step_controlled(self, nsteps: int = 1):
+        """nsteps x (apply_commands, one physics step): the reference's per-step command cadence."""
+        _check(lib().ss_batch_step_controlled(self._h, nsteps, C.c_void_p(self.command.data_ptr()),
+                                              C.c_void_p(self.base_state.data_ptr()), _stream()))
 
     def pull_status(self):
         _check(lib().ss_batch_pull_status(self._h, C.c_void_p(self.status.data_ptr()), _stream()))

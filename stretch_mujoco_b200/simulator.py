@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from . import engine, enums
-from .enums import COMMAND_SLOTS, STATUS_JOINTS, Actuators, StretchCameras, StretchSensors
+from .enums import COMMAND_SLOTS, STATUS_JOINTS, Actuators, StretchCameras, StretchSensors  # noqa: F401
 
 
 class PositionVelocity:
@@ -38,10 +38,113 @@ class StatusStretchJoints:
         self.base = BaseStatus(row[:, 17], row[:, 18], row[:, 19], row[:, 20], row[:, 21])
 
 
+class StatusStretchCameras:
+    """Field names and accessors of `datamodels/status_stretch_camera.py:10-133`; pixel arrays are torch CUDA
+    tensors with a leading env dimension: RGB uint8 [n, H, W, 3], depth float32 [n, H, W], in the camera's own
+    orientation and RGB order (what the reference's server produces).  `get_camera_data` applies the client-side
+    post-processing of the reference (np.rot90 of the d435i / nav images, RGB->BGR, JET depth colour map) unless
+    the frames were already rendered that way (`pull_camera_data(auto_rotate=..., auto_correct_rgb=...)`)."""
+    FIELDS = ("cam_d405_rgb", "cam_d405_depth", "cam_d435i_rgb", "cam_d435i_depth", "cam_nav_rgb")
+
+    def __init__(self, time=0.0, fps=0.0, prerotated: bool = False, prebgr: bool = False):
+        self.time, self.fps = time, fps
+        for n in self.FIELDS:
+            setattr(self, n, None)
+        self.cam_d405_K = None
+        self.cam_d435i_K = None
+        self._prerotated, self._prebgr = prerotated, prebgr
+
+    @staticmethod
+    def default():
+        return StatusStretchCameras(time=0, fps=0)
+
+    def set_camera_data(self, camera, data) -> None:
+        if camera.name not in self.FIELDS:
+            raise NotImplementedError(f"Camera {camera} is not implemented.")
+        setattr(self, camera.name, data)
+
+    def get_camera_data(self, camera, *, auto_rotate: bool = True, auto_correct_rgb: bool = True,
+                        use_depth_color_map: bool = False):
+        import torch
+        data = getattr(self, camera.name, None) if camera.name in self.FIELDS else None
+        if data is None:
+            raise ValueError(f"Tried to get {camera} data, but it is empty or not implemented.")
+        k = camera.value.rot90_k
+        if auto_rotate and k and not self._prerotated:
+            data = torch.rot90(data, k, dims=(1, 2))          # np.rot90(img, k) per env
+        if camera.value.is_depth:
+            if use_depth_color_map:
+                data = engine.depth_colormap(data)            # utils.get_depth_color_map (utils.py:363-373)
+        elif auto_correct_rgb and not self._prebgr:
+            data = data.flip(-1)                              # cv2.COLOR_RGB2BGR
+        return data
+
+    def get_all(self, *, auto_rotate: bool = True, auto_correct_rgb: bool = True, use_depth_color_map: bool = False) -> dict:
+        out = {}
+        for cam in StretchCameras.all():
+            try:
+                out[cam] = self.get_camera_data(cam, auto_rotate=auto_rotate, auto_correct_rgb=auto_correct_rgb,
+                                                use_depth_color_map=use_depth_color_map)
+            except ValueError:
+                pass
+        return out
+
+    def to_dict(self) -> dict:
+        d = {"time": self.time, "fps": self.fps, "cam_d405_K": self.cam_d405_K, "cam_d435i_K": self.cam_d435i_K}
+        d.update({n: getattr(self, n) for n in self.FIELDS})
+        return d
+
+    # dict-style access by StretchCameras member or field name (raw stored frames)
+    def __getitem__(self, key):
+        name = key if isinstance(key, str) else key.name
+        v = getattr(self, name, None)
+        if v is None:
+            raise KeyError(key)
+        return v
+
+    def __contains__(self, key):
+        name = key if isinstance(key, str) else key.name
+        return getattr(self, name, None) is not None
+
+
+class StatusStretchSensors:
+    """Field names and accessors of `datamodels/status_stretch_sensors.py:11-77`; values are [nenv, ...] tensors."""
+
+    def __init__(self, time=0.0, fps=0.0, base_gyro=None, base_imu=None, lidar=None):
+        self.time, self.fps, self.base_gyro, self.base_imu, self.lidar = time, fps, base_gyro, base_imu, lidar
+
+    @staticmethod
+    def default():
+        return StatusStretchSensors(time=0, fps=0)
+
+    def get_data(self, sensor):
+        data = {StretchSensors.base_gyro: self.base_gyro, StretchSensors.base_accel: self.base_imu,
+                StretchSensors.base_lidar: self.lidar}.get(sensor)
+        if data is None:
+            raise ValueError(f"Tried to get {sensor} data, but it is empty.")
+        return data
+
+    def set_data(self, sensor, value) -> None:
+        if sensor == StretchSensors.base_gyro:
+            self.base_gyro = value
+        elif sensor == StretchSensors.base_accel:
+            self.base_imu = value
+        elif sensor == StretchSensors.base_lidar:
+            self.lidar = value
+        else:
+            raise NotImplementedError(f"Sensor {sensor} is not implemented")
+
+    def to_dict(self) -> dict:
+        return {"time": self.time, "fps": self.fps, "base_gyro": self.base_gyro, "base_imu": self.base_imu, "lidar": self.lidar}
+
+    def __getitem__(self, sensor):
+        return self.get_data(sensor)
+
+
 class StretchMujocoSimulator:
     def __init__(self, scene_xml_path: str | None = None, model=None, camera_hz: float = 30,
                  cameras_to_use: list | None = None, start_translation=None, start_rotation_quat=None, *,
-                 nenv: int = 1, device: int = 0, model_blob: bytes | None = None, maxcon: int = 24,
+                 nenv: int = 1, device: int = 0, model_blob: bytes | None = None, maxcon: int = 32,
                  with_render: bool | None = None):
         self.scene_xml_path, self.model_blob = scene_xml_path, model_blob
         self.camera_hz = camera_hz
@@ -80,7 +183,8 @@ class StretchMujocoSimulator:
         self._act = {n: self.dmodel.name2id(engine.OBJ_ACTUATOR, n) for n in
                      ["lift", "arm", "head_pan", "head_tilt", "wrist_yaw", "wrist_pitch", "wrist_roll", "gripper",
                       "left_wheel_vel", "right_wheel_vel"]}
-        self._last_move_to: dict[str, object] = {}
+        self._last_move_to: dict[str, object] = {}   # per actuator: [nenv] tensor of the last move_to target (NaN = none)
+        self._base_busy, self._base_checked = False, 0
         self._running = True
         self.batch.forward()
         if home:
@@ -99,8 +203,22 @@ class StretchMujocoSimulator:
 
     # ------------------------------------------------------------------ stepping
     def step(self, nsteps: int = 1) -> None:
-        """Apply pending commands (P2), advance `nsteps` physics steps."""
+        """Apply pending commands (P2), advance `nsteps` physics steps.
+
+        The reference runs push_command + BaseController.update after EVERY mj_step
+        (mujoco_server.py:378-379,450-463).  Commands are edge-triggered, so for everything except a running
+        base move_by one application in front of the block of steps is equivalent; while a base
+        translate_by / rotate_by may be running (its stop test must be evaluated per step) the block is
+        stepped in the reference's cadence, one command pass per physics step."""
         self._require()
+        if self._base_busy:
+            self.batch.step_controlled(nsteps)
+            self._base_checked += nsteps
+            if self._base_checked >= 50:          # one small D2H read per 50 steps to leave the slow cadence
+                self._base_checked = 0
+                mode = self.batch.base_state[:, 0]
+                self._base_busy = bool(((mode == 1) | (mode == 2)).any())
+            return
         self.batch.apply_commands()
         self.batch.step(nsteps)
 
@@ -129,7 +247,12 @@ class StretchMujocoSimulator:
         if a.name not in COMMAND_SLOTS:
             raise NotImplementedError(f"Actuator {a.name} is not supported.")
         self._write(0, COMMAND_SLOTS.index(a.name), pos, env_ids)
-        self._last_move_to[a.name] = pos
+        import torch
+        tgt = self._last_move_to.get(a.name)
+        if tgt is None:
+            tgt = torch.full((self.nenv,), float("nan"), dtype=torch.float32, device=self.batch.qpos.device)
+            self._last_move_to[a.name] = tgt
+        tgt[slice(None) if env_ids is None else env_ids] = torch.as_tensor(pos, dtype=torch.float32, device=tgt.device)
 
     def move_by(self, actuator, pos, env_ids=None) -> None:
         self._require()
@@ -139,6 +262,8 @@ class StretchMujocoSimulator:
         if a.name not in COMMAND_SLOTS:
             raise NotImplementedError(f"Actuator {a.name} is not supported.")
         self._write(20, COMMAND_SLOTS.index(a.name), pos, env_ids)
+        if a in (Actuators.base_translate, Actuators.base_rotate):
+            self._base_busy, self._base_checked = True, 0
 
     def set_base_velocity(self, v_linear, omega, env_ids=None) -> None:
         self._require()
@@ -175,12 +300,18 @@ class StretchMujocoSimulator:
         return StatusStretchJoints(self.batch.pull_status())
 
     def pull_joint_limits(self) -> dict:
-        """{actuator name: (min, max)} like mujoco_server.update_joint_limits (mujoco_server.py:281-291)."""
+        """{Actuators: (min, max)} like MujocoServer.update_joint_limits (mujoco_server.py:281-291): every MJCF
+        joint that maps to an actuator (enums/actuators.py:60-122); later joints of the same actuator (the four
+        telescope segments) overwrite earlier ones, as in the reference."""
         self._require()
         rng = self.dmodel.get("jnt_range").reshape(-1, 2)
         out = {}
         for j in range(self.dmodel.njnt):
-            out[self.dmodel.id2name(engine.OBJ_JOINT, j)] = (float(rng[j, 0]), float(rng[j, 1]))
+            try:
+                act = enums.get_actuator_by_joint_names_in_mjcf(self.dmodel.id2name(engine.OBJ_JOINT, j))
+            except NotImplementedError:
+                continue
+            out[act] = (float(rng[j, 0]), float(rng[j, 1]))
         return out
 
     def get_base_pose(self):
@@ -199,18 +330,20 @@ class StretchMujocoSimulator:
     def get_ee_pose(self):
         return self.get_link_pose("link_grasp_center")
 
-    def pull_sensor_data(self) -> dict:
-        """gyro [nenv,3], accelerometer [nenv,3], lidar [nenv,nray] (status_stretch_sensors.py:11-77)."""
+    def pull_sensor_data(self) -> StatusStretchSensors:
+        """gyro [nenv,3], accelerometer [nenv,3], lidar [nenv,nray] as a `StatusStretchSensors`
+        (status_stretch_sensors.py:11-77; gathered like mujoco_server_sensor_manager.py:65-89)."""
         self._require()
-        out = {StretchSensors.base_gyro: self.batch.sensordata[:, 0:3], StretchSensors.base_accel: self.batch.sensordata[:, 3:6]}
+        out = StatusStretchSensors(time=self.batch.time, fps=0.0, base_gyro=self.batch.sensordata[:, 0:3],
+                                   base_imu=self.batch.sensordata[:, 3:6])
         if self.dmodel.nrange > 0:
-            out[StretchSensors.base_lidar] = self.batch.lidar()
+            out.lidar = self.batch.lidar()
         return out
 
     def pull_camera_data(self, cameras: list | None = None, width: int | None = None, height: int | None = None,
                          env_begin: int = 0, env_count: int | None = None, auto_rotate: bool = False,
-                         auto_correct_rgb: bool = False) -> dict:
-        """{StretchCameras: tensor}: RGB uint8 [n,H,W,3] or depth float32 [n,H,W] with the depth
+                         auto_correct_rgb: bool = False) -> StatusStretchCameras:
+        """`StatusStretchCameras` (indexable by StretchCameras member): RGB uint8 [n,H,W,3] or depth float32 [n,H,W] with the depth
         limit applied (camera_manager.py:127-143, utils.py:87-91).  By default images are in camera
         orientation, RGB order (what the reference's server produces).  `auto_rotate` / `auto_correct_rgb`
         apply what StatusStretchCameras.get_camera_data does on the client
@@ -220,7 +353,7 @@ class StretchMujocoSimulator:
         import torch
         cams = cameras if cameras is not None else self.cameras_to_use
         n = self.nenv - env_begin if env_count is None else env_count
-        out = {}
+        out = StatusStretchCameras(time=self.batch.time, fps=0.0, prerotated=auto_rotate, prebgr=auto_correct_rgb)
         for cam in cams:
             cs = cam.value
             cid = self.dmodel.name2id(engine.OBJ_CAMERA, cs.name_in_mjcf)
@@ -238,9 +371,9 @@ class StretchMujocoSimulator:
             else:
                 img = torch.empty(n, oh, ow, 3, dtype=torch.uint8, device=dev)
                 self.batch.render(cid, W, H, cs.fovy, img, None, 0.0, env_begin, n, rot90=rot, bgr=auto_correct_rgb)
-            out[cam] = img
-        out["cam_d405_K"] = enums.compute_K(58, 1280, 720)    # camera_manager.py:168-183
-        out["cam_d435i_K"] = enums.compute_K(42, 1920, 1080)
+            out.set_camera_data(cam, img)
+        out.cam_d405_K = enums.compute_K(58, 1280, 720)    # camera_manager.py:168-183
+        out.cam_d435i_K = enums.compute_K(42, 1920, 1080)
         return out
 
     # ------------------------------------------------------------------ blocking helpers
@@ -251,12 +384,12 @@ class StretchMujocoSimulator:
         a = self._slot(actuator)
         if a.name not in self._last_move_to:
             return True
-        target = torch.as_tensor(self._last_move_to[a.name], dtype=torch.float32, device=self.batch.qpos.device)
-        dt = float(self.dmodel.get("opt_timestep")[0])
+        target = self._last_move_to[a.name]           # [nenv]; NaN where this env never got a move_to for the actuator
+        dt = float(self.dmodel.get("opt_timestep").ravel()[0])
         for _ in range(int(timeout / (dt * 50)) + 1):
             self.step(50)
             pos = getattr(self.pull_status(), a.name).pos
-            if bool(torch.all(torch.abs(pos - target) <= position_tolerance)):
+            if bool(torch.all(torch.isnan(target) | (torch.abs(pos - target) <= position_tolerance))):
                 return True
         return False
 
@@ -264,7 +397,7 @@ class StretchMujocoSimulator:
                              position_tolerance: float = 1e-4) -> bool:
         import torch
         a = self._slot(actuator)
-        dt = float(self.dmodel.get("opt_timestep")[0])
+        dt = float(self.dmodel.get("opt_timestep").ravel()[0])
         n = max(int(check_interval / dt), 1)
         last = None
         for _ in range(int(timeout / check_interval) + 1):
