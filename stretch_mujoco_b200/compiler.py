@@ -630,3 +630,138 @@ def _collision_pairs(m: Model):
         margin[k] = max(A["geom_margin"][a], A["geom_margin"][b]); gap[k] = max(A["geom_gap"][a], A["geom_gap"][b])
     A["pair_condim"] = condim; A["pair_friction"] = fr; A["pair_solref"] = sref; A["pair_solimp"] = simp
     A["pair_margin"] = margin; A["pair_gap"] = gap
+
+
+# ----------------------------------------------------------------------------- real-mjModel import hook
+# the day a MuJoCo install is reachable, compile parity (this compiler vs
+# MjModel.from_xml_path) and step parity can be checked separately by loading a DUMP of the real mjModel through the
+# same blob format.  `dump_mjmodel_npz` runs where `import mujoco` works; `load_mjmodel_npz` runs anywhere.
+
+# mjModel attributes that map one-to-one onto this compiler's arrays
+_MJMODEL_FIELDS = [
+    "body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_geomnum",
+    "body_geomadr", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_gravcomp",
+    "body_invweight0", "body_subtreemass", "jnt_type", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "jnt_pos", "jnt_axis",
+    "jnt_stiffness", "jnt_range", "jnt_limited", "jnt_margin", "jnt_solref", "jnt_solimp", "qpos0", "qpos_spring",
+    "dof_bodyid", "dof_jntid", "dof_parentid", "dof_Madr", "dof_armature", "dof_damping", "dof_frictionloss", "dof_solref",
+    "dof_solimp", "dof_invweight0", "geom_type", "geom_contype", "geom_conaffinity", "geom_condim", "geom_bodyid", "geom_dataid",
+    "geom_priority", "geom_group", "geom_matid", "geom_size", "geom_aabb", "geom_pos", "geom_quat", "geom_friction", "geom_solref",
+    "geom_solimp", "geom_rgba", "geom_rbound", "geom_solmix", "geom_margin", "geom_gap", "site_bodyid", "site_pos", "site_quat",
+    "cam_bodyid", "cam_pos", "cam_quat", "cam_fovy", "light_bodyid", "light_pos", "light_dir", "light_directional", "light_ambient",
+    "light_diffuse", "light_specular", "tendon_adr", "tendon_num", "wrap_objid", "wrap_prm", "eq_obj1id", "eq_obj2id", "eq_data",
+    "eq_solref", "eq_solimp", "eq_active0", "actuator_trntype", "actuator_trnid", "actuator_gainprm", "actuator_biasprm",
+    "actuator_ctrlrange", "actuator_ctrllimited", "actuator_forcerange", "actuator_forcelimited", "sensor_type", "sensor_objid",
+    "sensor_adr", "sensor_dim", "sensor_cutoff", "key_ctrl", "key_qpos", "exclude_signature"]
+_MJ_SENSOR = {39: SENS_GYRO, 1: SENS_ACCEL, 7: SENS_RANGE}   # placeholders, overwritten by the dump's own enum table
+_OBJ_NAMES = {OBJ_BODY: "body", OBJ_JOINT: "jnt", OBJ_GEOM: "geom", OBJ_SITE: "site", OBJ_CAMERA: "cam", OBJ_ACTUATOR: "actuator",
+              OBJ_SENSOR: "sensor", OBJ_KEY: "key", OBJ_MESH: "mesh", OBJ_TENDON: "tendon"}
+
+
+def dump_mjmodel_npz(mjmodel, path: str) -> None:
+    """Run where `import mujoco` works: flat .npz of the named mjModel arrays this engine consumes."""
+    import mujoco
+    out = {}
+    for f in _MJMODEL_FIELDS:
+        if hasattr(mjmodel, f):
+            out[f] = np.asarray(getattr(mjmodel, f))
+    o = mjmodel.opt
+    out.update(opt_timestep=o.timestep, opt_gravity=np.asarray(o.gravity), opt_impratio=o.impratio, opt_tolerance=o.tolerance,
+               opt_ls_tolerance=o.ls_tolerance, opt_iterations=o.iterations, opt_ls_iterations=o.ls_iterations, opt_cone=int(o.cone),
+               opt_solver=int(o.solver), opt_multiccd=int(bool(o.enableflags & mujoco.mjtEnableBit.mjENBL_MULTICCD)),
+               stat_meaninertia=mjmodel.stat.meaninertia, stat_extent=mjmodel.stat.extent)
+    out["sensor_enum"] = np.array([int(mujoco.mjtSensor.mjSENS_GYRO), int(mujoco.mjtSensor.mjSENS_ACCELEROMETER),
+                                   int(mujoco.mjtSensor.mjSENS_RANGEFINDER)])
+    for k in ("mesh_vert", "mesh_vertadr", "mesh_vertnum", "mesh_graph", "mesh_graphadr", "actuator_gear"):
+        out[k] = np.asarray(getattr(mjmodel, k))
+    for objtype, prefix in _OBJ_NAMES.items():
+        mjobj = {"body": mujoco.mjtObj.mjOBJ_BODY, "jnt": mujoco.mjtObj.mjOBJ_JOINT, "geom": mujoco.mjtObj.mjOBJ_GEOM,
+                 "site": mujoco.mjtObj.mjOBJ_SITE, "cam": mujoco.mjtObj.mjOBJ_CAMERA, "actuator": mujoco.mjtObj.mjOBJ_ACTUATOR,
+                 "sensor": mujoco.mjtObj.mjOBJ_SENSOR, "key": mujoco.mjtObj.mjOBJ_KEY, "mesh": mujoco.mjtObj.mjOBJ_MESH,
+                 "tendon": mujoco.mjtObj.mjOBJ_TENDON}[prefix]
+        n = getattr(mjmodel, "n" + prefix)
+        out["names_" + prefix] = np.array([mujoco.mj_id2name(mjmodel, mjobj, i) or "" for i in range(n)])
+    np.savez_compressed(path, **out)
+
+
+def load_mjmodel_npz(path: str) -> Model:
+    """mjModel dump (dump_mjmodel_npz) -> `Model` with this compiler's array names; the candidate pair list, the
+    per-pair contact parameters and the hull tables are derived here the same way compile_scene derives them.
+    Physics only (no ray geometry)."""
+    Z = np.load(path, allow_pickle=False)
+    m = Model()
+    A = m.arrays
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    i32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+    ints = {"body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_geomnum",
+            "body_geomadr", "jnt_type", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "jnt_limited", "dof_bodyid", "dof_jntid",
+            "dof_parentid", "dof_Madr", "geom_type", "geom_contype", "geom_conaffinity", "geom_condim", "geom_bodyid", "geom_dataid",
+            "geom_priority", "geom_group", "geom_matid", "site_bodyid", "cam_bodyid", "light_bodyid", "light_directional", "tendon_adr",
+            "tendon_num", "wrap_objid", "eq_obj1id", "eq_obj2id", "eq_active0", "actuator_trntype", "actuator_trnid",
+            "actuator_ctrllimited", "actuator_forcelimited", "sensor_type", "sensor_objid", "sensor_adr", "sensor_dim", "exclude_signature"}
+    for f in _MJMODEL_FIELDS:
+        if f in Z.files:
+            A[f] = i32(Z[f]) if f in ints else f64(Z[f])
+    for k in ("opt_timestep", "opt_impratio", "opt_tolerance", "opt_ls_tolerance", "stat_meaninertia", "stat_extent"):
+        A[k] = f64([float(Z[k])])
+    A["opt_gravity"] = f64(Z["opt_gravity"])
+    for k in ("opt_iterations", "opt_ls_iterations", "opt_cone", "opt_solver", "opt_multiccd"):
+        A[k] = i32([int(Z[k])])
+    # mjModel keeps 3 gain / 3 bias parameters of 10, a 6-vector gear, row vectors for wrap_prm ... : trim to this engine's shapes
+    if "actuator_gear" in Z.files:
+        A["actuator_gear"] = f64(np.asarray(Z["actuator_gear"]).reshape(len(A["actuator_trnid"].reshape(-1, 2) if A["actuator_trnid"].ndim > 1 else A["actuator_trnid"]), -1)[:, 0])
+    if A["actuator_trnid"].ndim > 1:
+        A["actuator_trnid"] = i32(A["actuator_trnid"][:, 0])
+    for k in ("actuator_gainprm", "actuator_biasprm"):
+        A[k] = f64(A[k][:, :3])
+    if "sensor_enum" in Z.files:
+        gy, ac, rf = [int(x) for x in Z["sensor_enum"]]
+        A["sensor_type"] = i32([{gy: SENS_GYRO, ac: SENS_ACCEL, rf: SENS_RANGE}.get(int(t), -1) for t in A["sensor_type"]])
+    # convex hulls from the mesh graphs (graph = numvert, numface, vert_edgeadr[nv], vert_globalid[nv], edge_localid[nv + 3 nf], face_globalid[3 nf])
+    nmesh = len(Z["mesh_vertadr"]) if "mesh_vertadr" in Z.files else 0
+    hull_adr, hull_num, hull_verts, edge_adr, edges = [], [], [], [0], []
+    for k in range(nmesh):
+        ga = int(Z["mesh_graphadr"][k])
+        if ga < 0:
+            hull_adr.append(-1); hull_num.append(0)
+            continue
+        G = np.asarray(Z["mesh_graph"][ga:])
+        nvh, nfh = int(G[0]), int(G[1])
+        vert_edgeadr = G[2:2 + nvh]; vert_globalid = G[2 + nvh:2 + 2 * nvh]; edge_localid = G[2 + 2 * nvh:2 + 3 * nvh + 3 * nfh]
+        V = np.asarray(Z["mesh_vert"]).reshape(-1, 3)[int(Z["mesh_vertadr"][k]):][vert_globalid]
+        hull_adr.append(sum(len(h) for h in hull_verts)); hull_num.append(nvh); hull_verts.append(V.astype(np.float64))
+        for v in range(nvh):
+            e = int(vert_edgeadr[v])
+            while edge_localid[e] >= 0:
+                edges.append(int(edge_localid[e])); e += 1
+            edge_adr.append(len(edges))
+    A["mesh_hulladr"] = i32(hull_adr); A["mesh_hullnum"] = i32(hull_num)
+    A["hull_vert"] = f64(np.concatenate(hull_verts) if hull_verts else np.zeros((0, 3))).reshape(-1, 3)
+    A["hull_edgeadr"] = i32(edge_adr); A["hull_edge"] = i32(edges)
+    m.names = {objtype: [str(s) for s in Z["names_" + prefix]] if "names_" + prefix in Z.files else [] for objtype, prefix in _OBJ_NAMES.items()}
+    _collision_pairs(m)
+    nq, nv, nu = len(A["qpos0"]), len(A["dof_bodyid"]), len(A["actuator_trnid"])
+    nM = 0
+    for d in range(nv):
+        k = d
+        while k >= 0:
+            nM += 1
+            k = int(A["dof_parentid"][k])
+    A["sizes"] = i32([nq, nv, nu, len(A["body_parentid"]), len(A["jnt_type"]), len(A["geom_type"]), len(A["site_bodyid"]),
+                      len(A["cam_bodyid"]), len(A["tendon_adr"]), len(A["eq_obj1id"]), len(A["sensor_type"]),
+                      int(A["sensor_dim"].sum()) if len(A["sensor_dim"]) else 0, len(A["key_ctrl"]), nM,
+                      len(A["pair_geom1"]), nmesh])
+    return m
+
+
+def compare_models(ours: Model, theirs: Model, rtol: float = 1e-9) -> dict:
+    """{array name: max abs difference (or 'shape a vs b')} for every array the two models share: compile parity report."""
+    out = {}
+    for k, a in ours.arrays.items():
+        if k not in theirs.arrays:
+            continue
+        b = theirs.arrays[k]
+        if a.shape != b.shape:
+            out[k] = f"shape {a.shape} vs {b.shape}"
+        elif a.size and not np.allclose(a, b, rtol=rtol, atol=rtol):
+            out[k] = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+    return out

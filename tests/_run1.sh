@@ -1,3 +1,1 @@
-SS_VERBOSE=1 python tests/tune_physics.py 2>&1 | tail -2
-python tests/determinism_stress.py 2>&1 | tail -2
-python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+python -m pytest tests/test_parity_r2_gpu.py -m gpu -q -s -k "frames_actuators" 2>&1 | grep -v "^$" | grep -n "^E  \|Error\|passed\|failed\|>  " | cut -c1-300 | head -40

@@ -151,3 +151,62 @@ def test_kitchen_proxy_golden_matches_fresh_compile():
     m = scenes.compile_kitchen_proxy(with_render=True, lidar_rays=1000)
     for k in ("qpos0", "body_mass", "geom_size", "site_quat", "pair_geom1", "pair_geom2", "rmesh_face"):
         assert np.array_equal(np.asarray(m.arrays[k]), A[k]), k
+
+
+def test_mjmodel_npz_import_round_trip(tmp_path, blob_empty_floor):
+    """a dump of a real mjModel (flat .npz of named arrays) loads through the same path.  Without a
+    MuJoCo install the hook is exercised with a dump written from this compiler's own arrays in mjModel's layout
+    (mesh graphs, 10-wide actuator parameter rows, 6-vector gear, 2-column trnid)."""
+    from stretch_mujoco_b200 import blob as blobmod
+    A, names = blobmod.unpack(blob_empty_floor)
+    Z = {f: A[f] for f in compiler._MJMODEL_FIELDS if f in A}
+    nu = len(A["actuator_trnid"])
+    Z["actuator_trnid"] = np.stack([A["actuator_trnid"], -np.ones(nu, np.int32)], 1)
+    Z["actuator_gear"] = np.concatenate([A["actuator_gear"][:, None], np.zeros((nu, 5))], 1)
+    for k in ("actuator_gainprm", "actuator_biasprm"):
+        Z[k] = np.concatenate([A[k], np.zeros((nu, 7))], 1)
+    for k in ("opt_timestep", "opt_impratio", "opt_tolerance", "opt_ls_tolerance", "stat_meaninertia", "stat_extent",
+              "opt_iterations", "opt_ls_iterations", "opt_cone", "opt_solver", "opt_multiccd"):
+        Z[k] = A[k][0]
+    Z["opt_gravity"] = A["opt_gravity"]
+    Z["sensor_enum"] = np.array([compiler.SENS_GYRO, compiler.SENS_ACCEL, compiler.SENS_RANGE])
+    # mesh graphs in mjModel's layout from the hull tables
+    mesh_vert, vertadr, graph, graphadr = [], [], [], []
+    for k in range(len(A["mesh_hulladr"])):
+        vertadr.append(sum(len(v) for v in mesh_vert))
+        ha, hn = int(A["mesh_hulladr"][k]), int(A["mesh_hullnum"][k])
+        if ha < 0:
+            graphadr.append(-1); mesh_vert.append(np.zeros((1, 3)))
+            continue
+        mesh_vert.append(A["hull_vert"][ha:ha + hn])
+        ea = A["hull_edgeadr"][ha:ha + hn + 1]
+        edge_local, vert_edgeadr = [], []
+        for v in range(hn):
+            vert_edgeadr.append(len(edge_local))
+            edge_local += list(A["hull_edge"][ea[v]:ea[v + 1]]) + [-1]
+        nf = (len(edge_local) - hn + 2) // 3 + 1
+        edge_local += [-1] * (hn + 3 * nf - len(edge_local))
+        graphadr.append(len(graph))
+        graph += [hn, nf] + vert_edgeadr + list(range(hn)) + edge_local + [0] * (3 * nf)
+    Z.update(mesh_vert=np.concatenate(mesh_vert), mesh_vertadr=np.array(vertadr), mesh_vertnum=np.array([len(v) for v in mesh_vert]),
+             mesh_graph=np.array(graph), mesh_graphadr=np.array(graphadr))
+    for objtype, prefix in compiler._OBJ_NAMES.items():
+        Z["names_" + prefix] = np.array(names.get(objtype, []))
+    path = str(tmp_path / "mjmodel.npz")
+    np.savez_compressed(path, **Z)
+    m2 = compiler.load_mjmodel_npz(path)
+    ours = compiler.Model(); ours.arrays, ours.names = A, names
+    diff = compiler.compare_models(ours, m2)
+    assert diff == {}, diff
+    assert np.array_equal(m2.arrays["pair_geom1"], A["pair_geom1"]) and np.array_equal(m2.arrays["hull_edge"], A["hull_edge"])
+    assert np.array_equal(m2.arrays["sizes"], A["sizes"])
+    assert m2.name2id(compiler.OBJ_BODY, "base_link") == ours.name2id(compiler.OBJ_BODY, "base_link")
+    # and the imported model steps in the oracle exactly like the compiled one
+    from oracle.oracle import OracleModel
+    qs = []
+    for arrays, nm in ((A, names), (m2.arrays, m2.names)):
+        om = OracleModel(blobmod.pack(arrays, nm)); om.set_options(enable_lidar=False)
+        q = arrays["qpos0"][None].copy(); v = np.zeros((1, om.nv)); w = np.zeros((1, om.nv))
+        om.step(q, v, arrays["key_ctrl"][0][None].copy(), w, nsteps=50)
+        qs.append(q)
+    assert np.array_equal(qs[0], qs[1])

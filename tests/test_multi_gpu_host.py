@@ -55,6 +55,21 @@ def test_sharded_rollout_metrics_gloo():
 def test_reference_arm_runs_on_rank0_only(monkeypatch, capsys):
     import bench
     monkeypatch.setenv("RANK", "1")
-    class A: gpus = 2; steps = 1; warmup = 3; cpu_nenv = 4
-    bench.run_reference(A)
+    class A: gpus = 2; steps = 1; warmup = 3; cpu_nenv = 4; nenv = 4; config = "cfg2"; scaling = "weak"
+    bench.run_reference(A, bench.CONFIGS["cfg2"])
     assert capsys.readouterr().out == ""      # other ranks exit without work
+
+
+def test_reference_arm_line_and_strong_scaling_split(monkeypatch, capsys):
+    """Rank 0 of the reference arm prints the contract line; strong scaling splits --nenv over the ranks."""
+    import json
+    import bench
+    monkeypatch.setenv("RANK", "0")
+    class A: gpus = 1; steps = 1; warmup = 3; cpu_nenv = 8; nenv = 8; config = "cfg2"; scaling = "strong"
+    bench.run_reference(A, bench.CONFIGS["cfg2"])
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["scaling"] == "strong" and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    assert set(bench.CONFIGS) == {"cfg2", "default", "cfg3", "cfg4", "cfg5"}
+    for name, cfg in bench.CONFIGS.items():
+        assert os.path.exists(os.path.join(bench.GOLDEN_DIR, cfg["blob"])), name

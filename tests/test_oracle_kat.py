@@ -140,3 +140,75 @@ def test_solver_optimality_on_random_rollout_states(oracle_E, arrays_E):
             worst = max(worst, float((np.abs(r).max(1) / scale).max()))
             assert o["solver_iter"].max() < 50
     assert worst < 1e-5, worst
+
+
+def test_ray_primitives_closed_form(blob_default_scene):
+    """Pins the oracle's mj_ray restatement (row S2) on closed-form ray / primitive intersections in the
+    reference's default scene (models/scene.xml:21-35): floor plane, the table box (pos 0 -1 .24, half sizes
+    .6 .5 .24), the free cylinder object2 (radius .02, half height .04 at 0.08 -0.55 0.6) and a miss."""
+    import os
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    raw = blob.read_bytes(os.path.join(os.path.dirname(__file__), "golden", "stretch_default_scene_render.ssm.z"))   # with ray geometry
+    A, names = blob.unpack(raw)
+    om = OracleModel(raw)
+    om.set_options(enable_lidar=False)
+    q = A["qpos0"][None].copy()
+    o = om.forward(q, np.zeros((1, om.nv)), np.zeros((1, om.nu)), want=("xpos", "xquat"))
+    gname = names[compiler.OBJ_GEOM]
+    body = names[compiler.OBJ_BODY]
+    gb = A["geom_bodyid"]
+    org = np.array([[[5.0, 5.0, 2.0], [0.3, -1.2, 2.0], [2.0, -1.2, 0.24], [0.08, -0.55, 2.0], [5.0, 5.0, 2.0], [0.3, -1.2, 2.0]]])
+    drc = np.array([[[0, 0, -1.0], [0, 0, -1.0], [-1.0, 0, 0], [0, 0, -1.0], [0, 0, 1.0], [0, 0.28, -0.96]]])
+    dist, geom = om.rays(o["xpos"], o["xquat"], org, drc, groupmask=0, bodyexclude=-1)
+    d, g = dist[0], geom[0]
+    assert d[0] == pytest.approx(2.0, abs=1e-12) and gname[g[0]] == "floor"
+    assert d[1] == pytest.approx(2.0 - 0.48, abs=1e-12) and body[gb[g[1]]] == "table"          # top face of the table
+    assert d[2] == pytest.approx(2.0 - 0.6, abs=1e-12) and body[gb[g[2]]] == "table"           # +x side face
+    assert d[3] == pytest.approx(2.0 - 0.64, abs=1e-12) and body[gb[g[3]]] == "object2"        # top cap of the cylinder
+    assert d[4] == -1.0 and g[4] == -1                                                         # looking at the sky
+    # oblique ray onto the table top: z drops 1.52 at 0.96 per unit length (lands at y = -0.757, inside the top face)
+    assert d[5] == pytest.approx(1.52 / 0.96, abs=1e-12) and body[gb[g[5]]] == "table"
+
+
+def test_camera_sky_colour_anchor():
+    """Weak colour anchor (docs/getting_started.ipynb:414-416): the top rows of the wrist d405 RGB frame show the sky,
+    `[169, 224, 255]` in the reference (gradient skybox 0.44 0.80 1.00 -> white, plus haze).  The restated
+    renderer draws the gradient without haze: blue saturated, R < G < B, within 60 counts of the printed value."""
+    import os
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    raw = blob.read_bytes(os.path.join(os.path.dirname(__file__), "golden", "stretch_default_scene_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    om = OracleModel(raw)
+    om.set_options(enable_lidar=False)
+    q = A["qpos0"][None].copy(); v = np.zeros((1, om.nv)); w = np.zeros((1, om.nv))
+    o = om.step(q, v, A["key_ctrl"][0][None].copy(), w, nsteps=1600, want=("xpos", "xquat"))       # t = 3.2 s
+    cam = names[compiler.OBJ_CAMERA].index("d405_rgb")
+    rgb, depth = om.render(o["xpos"], o["xquat"], cam, 96, 54, 58.0)
+    top = rgb[0, 0].astype(float).mean(0)
+    assert top[2] > 240 and top[0] < top[1] < top[2]
+    assert np.abs(top - np.array([169, 224, 255])).max() < 60, top
+
+
+def test_startup_base_drift_anchor(blob_default_scene):
+    """The only contact-sensitive number the reference printed: after `home` from qpos0 in the default scene the base
+    has been kicked to x = -0.0122, y = 0.0044, theta = -0.0650 by t = 8.26 s (docs/getting_started.ipynb:729-751) --
+    the stowed wrist interpenetrates the base hull by 5 cm at qpos0 and is pushed out through MPR + multiccd contacts
+    in the first ~50 steps.  That transient is chaotic (profiles/parity_r2.md: two fp64 oracle runs that differ by
+    fp32 rounding separate within tens of steps), so the anchor pins the SIZE and DIRECTION of the kick, not its
+    digits: the oracle gives x = -0.0061, y = +0.0054, theta = +0.020 (before multiccd / multi-point plane-mesh
+    contacts existed in the oracle the base did not move at all)."""
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    A, _ = blob.unpack(blob_default_scene)
+    om = OracleModel(blob_default_scene)
+    om.set_options(enable_lidar=False)
+    q = A["qpos0"][None].copy(); v = np.zeros((1, om.nv)); w = np.zeros((1, om.nv)); t = np.zeros(1)
+    om.step(q, v, A["key_ctrl"][0][None].copy(), w, t, nsteps=4130)
+    x, y = q[0, 0], q[0, 1]
+    theta = np.arctan2(2 * (q[0, 3] * q[0, 6] + q[0, 4] * q[0, 5]), 1 - 2 * (q[0, 5] ** 2 + q[0, 6] ** 2))
+    assert -0.0122 * 3 < x < -0.0122 / 3                  # kicked backwards by about a centimetre
+    assert 0.0044 / 3 < y < 0.0044 * 3                    # and a few millimetres to the left
+    assert abs(theta) < 0.0650 * 1.5                      # yaw of the same order (its sign is not reproduced)
+    assert np.abs(v[0, :6]).max() < 1e-6                  # and the base is at rest again (reference: ~1e-8)

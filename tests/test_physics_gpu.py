@@ -64,7 +64,10 @@ def test_forward_matches_oracle_at_qpos0(gpu, oracle_E, arrays_E):
     plane = A["geom_type"][np.maximum(cg[:, :, 0], 0)] == 0
     assert dd[first | plane].max() < 1e-6 and dd.max() < 5e-4
     qs = B.dbg["qacc_smooth"].cpu().numpy()
-    assert np.abs(qs - o["qacc_smooth"]).max() <= 1e-3 * np.abs(o["qacc_smooth"]).max()
+    e = qs - o["qacc_smooth"]
+    en = np.sqrt(np.einsum("ei,eij,ej->e", e, o["M"], e) / np.einsum("ei,eij,ej->e", o["qacc_smooth"], o["M"], o["qacc_smooth"]))
+    assert en.max() < 1e-5, en.max()                  # energy norm; component-wise the 8e-7 kg m^2 rubber tips set the fp32 floor:
+    assert np.abs(e).max() <= 1e-3 * np.abs(o["qacc_smooth"]).max()
     fc = B.dbg["qfrc_constraint"].cpu().numpy()
     assert np.abs(fc - o["qfrc_constraint"]).max() <= 1e-3 * np.abs(o["qfrc_constraint"]).max()
 
