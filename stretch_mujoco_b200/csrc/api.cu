@@ -34,7 +34,9 @@ extern "C" const char* ss_version(void) { return "stretchsim 0.1.0 (sm_100a)"; }
 
 extern "C" __global__ void ss_smooth_kernel(DevModel m, StepArgs a);
 extern "C" __global__ void ss_narrow_kernel(DevModel m, StepArgs a);
-extern "C" __global__ void ss_solve_kernel(DevModel m, StepArgs a);
+int ss_solve_tile(int nv);
+cudaError_t ss_solve_set_smem(int tile, int bytes);
+void ss_solve_launch(int tile, int grid, int block, size_t smem, cudaStream_t st, const DevModel& m, const StepArgs& a);
 #define NP_SMEM 96   // floats of shared memory per warp of the narrowphase kernel (physics.cu)
 #define NARROW_THREADS 256
 
@@ -99,7 +101,8 @@ static int build_layout(DevModel& m, int kernel) {
   int off = 0;
   auto take = [&](int n) { int r = off; off += (n + 3) & ~3; return r; };
   int nv = m.nv, nb = m.nbody;
-  o.ldm = nv <= 32 ? ((nv + 3) & ~3) : (nv | 1);   // n <= 32: float4 rows (register Cholesky path); else odd stride (scalar, conflict-free)
+  o.ldm = (nv + 3) & ~3;                           // float4 rows (register-tile Cholesky: one row per lane up to 32 dofs, two up to 64)
+  if (nv > 32 && ((o.ldm >> 2) & 1) == 0) o.ldm += 4;   // odd number of 16-byte chunks per row: conflict-free row-per-lane float4 access
   o.ldj = (nv + 3) & ~3;   // 16-byte aligned rows (float4 operand loads in the Hessian build)
   // persistent block, part A (staged in shared memory by the solve kernel) ...
   o.qpos = take(m.nq); o.qvel = take(nv); o.warm = take(nv);
@@ -116,6 +119,7 @@ static int build_layout(DevModel& m, int kernel) {
     o.xmat = take(nb * 9); o.cinert = take(nb * 10);
     o.cacc = take(nb * 10); o.cfrc = take(nb * 6);
     o.crb = o.cacc;                      // composite inertias (10/body) die before the RNE accelerations (6/body) are born
+    o.dpos = take(nb * 3); o.danchor = take(nv * 3);
   } else {
     off = o.pbA;                         // part B stays in global memory: its offsets are only valid against the global block
     o.qacc = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
@@ -124,7 +128,7 @@ static int build_layout(DevModel& m, int kernel) {
     o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxsimple); o.e_info = take(m.maxrow);   // friction loss: simple rows only
     o.J = take(std::max(m.maxcrow * o.ldj, nb * 6));
     o.cacc = o.J;                        // the IMU pass rebuilds body accelerations after the solve, when J is dead
-    o.H = take(nv * o.ldm); o.tmpJ = take((nv <= 32 ? 2 : 6) * o.ldj);   // register-tile path stages two vectors, the shared-memory path a cone block
+    o.H = take(nv * o.ldm); o.tmpJ = take(2 * o.ldj);   // the register-tile Hessian build stages two vectors per cone block
     o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
     o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
   }
@@ -478,7 +482,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   B->cost_w = 16; B->cost_scale = 1;
   if (const char* e = getenv("SS_COSTW")) B->cost_w = atoi(e);
   if (const char* e = getenv("SS_COSTSCALE")) B->cost_scale = atoi(e);
-  B->nsets = nenv >= 8 * sms ? 2 : 1;   // measured at 4096 envs: 1 set 53.2 ms, 2 sets 48.9 ms, 4 sets 48.8 ms per 50 steps
+  B->nsets = nenv >= 16 * sms ? 3 : nenv >= 8 * sms ? 2 : 1;   // measured at 4096 envs (round 2, three-kernel pipeline): 1 set 45.9 ms, 2 sets 43.2 ms, 3 sets 41.6 ms, 4 sets 41.9 ms per 50 steps
   if (const char* e = getenv("SS_SETS")) B->nsets = std::max(1, std::min(SS_MAXSETS, atoi(e)));
   if (B->nsets > 1) {
     bool ok = cudaEventCreateWithFlags(&B->ev_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -541,7 +545,8 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   const size_t smem2 = B->pack_bytes + (NARROW_THREADS / 32) * NP_SMEM * sizeof(float);
   CUDA_OK(cudaFuncSetAttribute(ss_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   CUDA_OK(cudaFuncSetAttribute(ss_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  CUDA_OK(cudaFuncSetAttribute(ss_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  const int tile = ss_solve_tile(B->dm.nv);
+  CUDA_OK(ss_solve_set_smem(tile, (int)smem3));
   // One mj_step = schedule_kernel (cost-sorted env order, counters) -> ss_smooth_kernel -> ss_narrow_kernel ->
   // ss_solve_kernel.  The env batch is cut into `nsets` contiguous sets whose launch chains run on library-owned
   // side streams, forked from and joined back into the caller's stream by events: one set's kernels fill the SMs
@@ -566,7 +571,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
       int g3 = std::min((a.nenv + B->warps_per_block - 1) / B->warps_per_block, B->grid);
       ss_smooth_kernel<<<g1, B->warps_per_block1 * 32, smem1, st>>>(B->dm1, a);
       ss_narrow_kernel<<<B->grid2, NARROW_THREADS, smem2, st>>>(B->dm1, a);
-      ss_solve_kernel<<<g3, B->warps_per_block * 32, smem3, st>>>(B->dm, a);
+      ss_solve_launch(tile, g3, B->warps_per_block * 32, smem3, st, B->dm, a);
       B->launches += 4;
     }
   }

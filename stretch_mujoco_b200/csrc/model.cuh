@@ -38,6 +38,7 @@ struct EnvLayout {
   int pb;                                        // size of the persistent block (multiple of 4)
   // smooth kernel only
   int xmat, cinert, crb, cfrc;
+  int dpos, danchor;                             // body origin relative to the parent's origin; hinge anchors relative to the body origin
   int cacc;                                      // smooth kernel: RNE accelerations; solve kernel: rebuilt with qacc for the IMU
   // solve kernel only
   int qacc, qacc_smooth, qfrc_con;

@@ -120,56 +120,6 @@ __device__ __forceinline__ bool group_sync_or(int bar, bool pred) {
 }
 
 // ----------------------------------------------------------------------------- dense algebra (single copies)
-// in-place Cholesky of the dense n x n matrix A (row stride ld, lower triangle) in shared memory.
-// Lane i owns row i (+32 for n > 32); left-looking so that only finished columns are read.
-__device__ __noinline__ void chol_factor(float* A, int n, int ld, int lane) {
-  for (int j = 0; j < n; j++) {
-    float s[2] = {0, 0};
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-      int i = lane + 32 * t;
-      if (i >= j && i < n) {
-        float acc = A[i * ld + j];
-        const float *ri = A + i * ld, *rj = A + j * ld;
-        for (int k = 0; k < j; k++) acc -= ri[k] * rj[k];
-        s[t] = acc;
-      }
-    }
-    float piv = __shfl_sync(FULL, (j < 32) ? s[0] : s[1], j & 31);
-    piv = sqrtf(fmaxf(piv, MINVAL));
-    float inv = 1.0f / piv;
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-      int i = lane + 32 * t;
-      if (i >= j && i < n) A[i * ld + j] = (i == j) ? piv : s[t] * inv;
-    }
-    __syncwarp();
-  }
-}
-
-// solve L L^T x = b in place; x is a shared-memory vector of length n
-__device__ __noinline__ void chol_solve(const float* L, float* x, int n, int ld, int lane) {
-  for (int j = 0; j < n; j++) {
-    float xj = x[j] / L[j * ld + j];
-    __syncwarp();
-    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
-      if (i == j) x[i] = xj;
-      else if (i > j) x[i] -= L[i * ld + j] * xj;
-    }
-    __syncwarp();
-  }
-  for (int j = n - 1; j >= 0; j--) {
-    float xj = x[j] / L[j * ld + j];
-    __syncwarp();
-    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
-      if (i == j) x[i] = xj;
-      else if (i < j) x[i] -= L[j * ld + i] * xj;
-    }
-    __syncwarp();
-  }
-}
-
 // y = A x for the symmetric dense matrix in shared memory (full storage).  Row stride a multiple of 4
 // (the n <= 32 layout): lane i reads row i and x as float4 (conflict-free: 7 * lane mod 8 is a
 // permutation), the tail below n scalar.
@@ -376,78 +326,6 @@ __device__ __noinline__ void mul_JT(const Rows R, float* y, const float* f, int 
   __syncwarp();
 }
 
-// H = M + J^T D J over quadratic rows + elliptic cone blocks (lane i owns row i of the lower
-// triangle), then Cholesky-factored in place.
-__device__ __noinline__ void build_hessian(const Rows R, float* H, const float* M, float* tmpJ, int ld, int lane) {
-  int nv = R.nv, ldj = R.ldj, ns = R.ns;
-  _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
-    float* Hi = H + i * ld;
-    const float* Mi = M + i * ld;
-    for (int k = 0; k <= i; k++) Hi[k] = Mi[k];
-    for (int r = 0; r < ns; r++) {
-      if (INFO_STATE(R.info[r]) != ST_QUADRATIC) continue;
-      int d1 = R.sd1[r], d2 = R.sd2[r];
-      float D = R.eD[r], c1 = R.sc1[r], c2 = R.sc2[r];
-      if (d1 == i) Hi[i] += D * c1 * c1;
-      if (d2 == i) Hi[i] += D * c2 * c2;
-      if (d2 >= 0) {
-        int hi = max(d1, d2), lo = min(d1, d2);
-        if (hi == i) Hi[lo] += D * c1 * c2;
-      }
-    }
-  }
-  for (int r = ns; r < R.nefc; r++) {
-    int inf = R.info[r], st = INFO_STATE(inf);
-    if (st == ST_QUADRATIC) {
-      const float* Jr = R.J + (r - ns) * ldj;
-      float D = R.eD[r];
-      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
-        float s = D * Jr[i];
-        if (s != 0) {
-          float* Hi = H + i * ld;
-          for (int k = 0; k <= i; k++) Hi[k] += s * Jr[k];
-        }
-      }
-    } else if (st == ST_CONE) {
-      const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
-      int dim = __float_as_int(con[C_DIM]);
-      float mu = con[C_MU], U[6], sc[6], T2 = 0, Hc[36];
-      sc[0] = mu; U[0] = R.jar[r] * mu;
-      for (int j = 1; j < dim; j++) { sc[j] = con[C_FRICTION + j - 1]; U[j] = R.jar[r + j] * sc[j]; T2 += U[j] * U[j]; }
-      float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
-      float iT = 1.0f / T;
-      Hc[0] = Dm;
-      for (int j = 1; j < dim; j++) Hc[j] = Hc[j * dim] = -Dm * mu * U[j] * iT;
-      for (int j = 1; j < dim; j++)
-        for (int k = 1; k < dim; k++)
-          Hc[j * dim + k] = Dm * (mu * N * U[j] * U[k] * iT * iT * iT - (j == k ? mu * (N - mu * T) * iT : 0.f));
-      for (int j = 0; j < dim; j++) for (int k = 0; k < dim; k++) Hc[j * dim + k] *= sc[j] * sc[k];
-      const float* Jc = R.J + (r - ns) * ldj;
-      __syncwarp();
-      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32)
-        for (int j = 0; j < dim; j++) {
-          float t = 0;
-          for (int k = 0; k < dim; k++) t += Hc[j * dim + k] * Jc[k * ldj + i];
-          tmpJ[j * ldj + i] = t;
-        }
-      __syncwarp();
-      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
-        float* Hi = H + i * ld;
-        for (int j = 0; j < dim; j++) {
-          float s = Jc[j * ldj + i];
-          if (s != 0) {
-            const float* tj = tmpJ + j * ldj;
-            for (int k = 0; k <= i; k++) Hi[k] += s * tj[k];
-          }
-        }
-      }
-      r += dim - 1;
-    }
-  }
-  __syncwarp();
-  chol_factor(H, nv, ld, lane);
-}
-
 // n <= 32 variant: the sparse rows are folded into a shared-memory copy of M, then lane i pulls row i
 // into registers (float4 loads), accumulates the dense contact rows as rank-1 updates (one unrolled body
 // shared by quadratic rows and cone blocks), factors in registers and solves H x = b for the vector xs in
@@ -535,51 +413,243 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
   if (work) chol_solve_rows<NT>(h, H, nv, ld, xs, lane);
   return any;
 }
-// dispatch on the register tile (28 columns cover the Stretch robot's nv = 26 with 24 % fewer pair updates)
-__device__ __forceinline__ bool hessian_solve32(const Rows& R, float* H, const float* M, float* tmpJ, int ld, float* xs, int lane,
-                                                bool alive, bool work, int sync) {
-  if (R.nv <= 28 && R.ldj <= 28) return hessian_solve<28>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
-  return hessian_solve<32>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
+// ---- 32 < n <= 64: TWO matrix rows per lane (row `lane` with its 32 leading columns in a0, row 32 + lane with
+// NT2 columns in a1).  Same right-looking scheme: the column shuffles of the first tile serve both rows, the
+// trailing columns 32.. only live in the second tile.  Rows in [n, NT2) are identity rows, rows >= NT2 are zero.
+template <int NT2>
+__device__ __forceinline__ void rank1_row2(float (&a0)[32], float (&a1)[NT2], float s0, float s1, const float* v, int ldv) {
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+#pragma unroll
+  for (int k = 0; k < NT2 / 4; k++) {
+    float4 t = (4 * k < ldv) ? v4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < 8) {
+      a0[4 * k] = fmaf(s0, t.x, a0[4 * k]); a0[4 * k + 1] = fmaf(s0, t.y, a0[4 * k + 1]);
+      a0[4 * k + 2] = fmaf(s0, t.z, a0[4 * k + 2]); a0[4 * k + 3] = fmaf(s0, t.w, a0[4 * k + 3]);
+    }
+    a1[4 * k] = fmaf(s1, t.x, a1[4 * k]); a1[4 * k + 1] = fmaf(s1, t.y, a1[4 * k + 1]);
+    a1[4 * k + 2] = fmaf(s1, t.z, a1[4 * k + 2]); a1[4 * k + 3] = fmaf(s1, t.w, a1[4 * k + 3]);
+  }
+}
+template <int NT2>
+__device__ __forceinline__ void chol_solve_rows2(float (&a0)[32], float (&a1)[NT2], float* Ls, int n, int ld, float* xs, int lane) {
+  constexpr int N1 = NT2 - 32;
+  const bool has1 = 32 + lane < n;
+  float x0 = xs[lane], x1 = has1 ? xs[32 + lane] : 0.f, rinv0 = 1.f, rinv1 = 1.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    float piv = __shfl_sync(FULL, a0[j], j);
+    float rinv = rsqrtf(fmaxf(piv, MINVAL));
+    float l0 = a0[j] * rinv, l1 = a1[j] * rinv;
+    a0[j] = l0; a1[j] = l1;
+    float yj = __shfl_sync(FULL, x0, j) * rinv;
+    if (lane == j) { rinv0 = rinv; x0 = yj; }
+    if (lane > j) x0 = fmaf(-l0, yj, x0);
+    x1 = fmaf(-l1, yj, x1);
+#pragma unroll
+    for (int k = j + 1; k < 32; k++) {
+      float t = __shfl_sync(FULL, l0, k);
+      a0[k] = fmaf(-l0, t, a0[k]); a1[k] = fmaf(-l1, t, a1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < N1; k++) a1[32 + k] = fmaf(-l1, __shfl_sync(FULL, l1, k), a1[32 + k]);
+  }
+#pragma unroll
+  for (int j = 32; j < NT2; j++) {
+    float piv = __shfl_sync(FULL, a1[j], j - 32);
+    float rinv = rsqrtf(fmaxf(piv, MINVAL));
+    float l1 = a1[j] * rinv;
+    a1[j] = l1;
+    float yj = __shfl_sync(FULL, x1, j - 32) * rinv;
+    if (lane == j - 32) { rinv1 = rinv; x1 = yj; }
+    if (lane > j - 32) x1 = fmaf(-l1, yj, x1);
+#pragma unroll
+    for (int k = j + 1; k < NT2; k++) a1[k] = fmaf(-l1, __shfl_sync(FULL, l1, k - 32), a1[k]);
+  }
+  {
+    float4* L4 = reinterpret_cast<float4*>(Ls + lane * ld);
+#pragma unroll
+    for (int k = 0; k < 8; k++) L4[k] = make_float4(a0[4 * k], a0[4 * k + 1], a0[4 * k + 2], a0[4 * k + 3]);
+    if (has1) {
+      float4* L41 = reinterpret_cast<float4*>(Ls + (32 + lane) * ld);
+#pragma unroll
+      for (int k = 0; k < NT2 / 4; k++)
+        if (4 * k < ld) L41[k] = make_float4(a1[4 * k], a1[4 * k + 1], a1[4 * k + 2], a1[4 * k + 3]);
+    }
+  }
+  __syncwarp();
+  // backward substitution: column `lane` (and 32 + lane) of L below the diagonal, one conflict-free load per row
+  float lj0[NT2], lj1[N1];
+#pragma unroll
+  for (int j = 0; j < NT2; j++) lj0[j] = (j < n && lane < j) ? Ls[j * ld + lane] : 0.f;
+#pragma unroll
+  for (int j = 32; j < NT2; j++) lj1[j - 32] = (j < n && 32 + lane < j) ? Ls[j * ld + 32 + lane] : 0.f;
+#pragma unroll
+  for (int j = NT2 - 1; j >= 32; j--) {
+    float xj = __shfl_sync(FULL, x1 * rinv1, j - 32);
+    x1 = (lane == j - 32) ? xj : fmaf(-lj1[j - 32], xj, x1);
+    x0 = fmaf(-lj0[j], xj, x0);
+  }
+#pragma unroll
+  for (int j = 31; j >= 0; j--) {
+    float xj = __shfl_sync(FULL, x0 * rinv0, j);
+    x0 = (lane == j) ? xj : fmaf(-lj0[j], xj, x0);
+  }
+  xs[lane] = x0;
+  if (has1) xs[32 + lane] = x1;
+  __syncwarp();
+}
+
+// H = M + J^T D J, factor, solve: the 32 < n <= NT2 counterpart of hessian_solve (same contract)
+template <int NT2>
+__device__ __noinline__ bool hessian_solve2(const Rows R, float* H, const float* M, float* tmpJ, int ld, float* xs, int lane,
+                                            bool alive, bool work, int sync) {
+  int nv = R.nv, ldj = R.ldj, ns = R.ns;
+  const bool has1 = 32 + lane < nv;
+  float h0[32], h1[NT2];
+  if (work) {
+    if (H != M) copy_matrix(H, M, nv, ld, lane);
+#pragma unroll 1
+    for (int i = lane; i < nv; i += 32) {
+      float* Hi = H + i * ld;
+#pragma unroll 1
+      for (int r = 0; r < ns; r++) {
+        if (INFO_STATE(R.info[r]) != ST_QUADRATIC) continue;
+        int d1 = R.sd1[r], d2 = R.sd2[r];
+        float D = R.eD[r], c1 = R.sc1[r], c2 = R.sc2[r];
+        if (d1 == i) Hi[i] += D * c1 * c1;
+        if (d2 == i) Hi[i] += D * c2 * c2;
+        if (d2 >= 0 && max(d1, d2) == i) Hi[min(d1, d2)] += D * c1 * c2;
+      }
+    }
+    __syncwarp();
+    {
+      const float4* H4 = reinterpret_cast<const float4*>(H + lane * ld);
+#pragma unroll
+      for (int k = 0; k < 8; k++) { float4 t = H4[k]; h0[4 * k] = t.x; h0[4 * k + 1] = t.y; h0[4 * k + 2] = t.z; h0[4 * k + 3] = t.w; }
+      const float4* H41 = reinterpret_cast<const float4*>(H + (has1 ? 32 + lane : 0) * ld);
+#pragma unroll
+      for (int k = 0; k < NT2 / 4; k++) {
+        float4 t = (has1 && 4 * k < ld) ? H41[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        h1[4 * k] = t.x; h1[4 * k + 1] = t.y; h1[4 * k + 2] = t.z; h1[4 * k + 3] = t.w;
+      }
+      if (!has1) {
+#pragma unroll
+        for (int k = 32; k < NT2; k++) h1[k] = (k == 32 + lane) ? 1.f : 0.f;
+      } else {
+#pragma unroll
+        for (int k = 32; k < NT2; k++) if (k >= nv) h1[k] = 0.f;   // row padding behind column nv
+      }
+    }
+#pragma unroll 1
+    for (int r = ns; r < R.nefc; r++) {
+      int inf = R.info[r], st = INFO_STATE(inf);
+      if (st == ST_QUADRATIC) {
+        const float* Jr = R.J + (r - ns) * ldj;
+        float D = R.eD[r];
+        rank1_row2<NT2>(h0, h1, D * Jr[lane], has1 ? D * Jr[32 + lane] : 0.f, Jr, ldj);
+      } else if (st == ST_CONE) {
+        const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+        int dim = __float_as_int(con[C_DIM]);
+        float mu = con[C_MU], U[6], sc[6], T2 = 0;
+        sc[0] = mu; U[0] = R.jar[r] * mu;
+#pragma unroll
+        for (int j = 1; j < 6; j++) {
+          sc[j] = j < dim ? con[C_FRICTION + j - 1] : 0.f; U[j] = j < dim ? R.jar[r + j] * sc[j] : 0.f; T2 += U[j] * U[j];
+        }
+        float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
+        float iT = 1.0f / T;
+        const float* Jc = R.J + (r - ns) * ldj;
+        float c = -Dm * mu * (N - mu * T) * iT;   // see hessian_solve for the rank-1 form of the cone Hessian
+        int j1 = has1 ? 32 + lane : lane;
+        float vg0 = mu * Jc[lane], vu0 = 0, vg1 = mu * Jc[j1], vu1 = 0;
+#pragma unroll
+        for (int j = 1; j < 6; j++) {
+          if (j < dim) {
+            float w = sc[j] * U[j] * iT, Ja = Jc[j * ldj + lane], Jb = Jc[j * ldj + j1];
+            vu0 = fmaf(w, Ja, vu0); vg0 = fmaf(-mu * w, Ja, vg0);
+            vu1 = fmaf(w, Jb, vu1); vg1 = fmaf(-mu * w, Jb, vg1);
+          }
+        }
+        if (!has1) { vg1 = 0.f; vu1 = 0.f; }
+        __syncwarp();
+        tmpJ[lane] = vg0; tmpJ[ldj + lane] = vu0;
+        if (32 + lane < ldj) { tmpJ[32 + lane] = vg1; tmpJ[ldj + 32 + lane] = vu1; }
+        __syncwarp();
+        rank1_row2<NT2>(h0, h1, Dm * vg0, Dm * vg1, tmpJ, ldj);
+        rank1_row2<NT2>(h0, h1, -c * vu0, -c * vu1, tmpJ + ldj, ldj);
+#pragma unroll 1
+        for (int j = 1; j < dim; j++) {
+          float fj = con[C_FRICTION + j - 1], cf = c * fj * fj;
+          rank1_row2<NT2>(h0, h1, cf * Jc[j * ldj + lane], has1 ? cf * Jc[j * ldj + 32 + lane] : 0.f, Jc + j * ldj, ldj);
+        }
+        r += dim - 1;
+      }
+    }
+  }
+  bool any = sync ? group_sync_or(sync, alive) : alive;
+  if (work) chol_solve_rows2<NT2>(h0, h1, H, nv, ld, xs, lane);
+  return any;
+}
+
+// One register tile per solve-kernel instantiation (TILE <= 32: one row per lane, TILE columns; TILE > 32: two rows
+// per lane).  28 columns cover the Stretch robot's nv = 26 with 24 % fewer pair updates than 32; 44 is the
+// reference's default scene (robot + three free bodies).  The host picks the kernel (ss_solve_tile).
+template <int TILE>
+__device__ __forceinline__ bool hessian_solve_any(const Rows& R, float* H, const float* M, float* tmpJ, int ld, float* xs, int lane,
+                                                  bool alive, bool work, int sync) {
+  if constexpr (TILE <= 32) return hessian_solve<TILE>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
+  else return hessian_solve2<TILE>(R, H, M, tmpJ, ld, xs, lane, alive, work, sync);
 }
 // x = A^-1 b for an SPD matrix in shared memory (factor left in A)
-__device__ __forceinline__ void chol_solve32(float* A, int n, int ld, float* xs, int lane, bool work, int sync) {
+template <int TILE>
+__device__ __forceinline__ void chol_solve_any(float* A, int n, int ld, float* xs, int lane, bool work, int sync) {
   Rows R;
   R.nv = n; R.ns = 0; R.nefc = 0; R.ldj = (n + 3) & ~3;
   R.sd1 = R.sd2 = nullptr; R.info = nullptr; R.sc1 = R.sc2 = R.J = R.eD = R.eR = R.efl = R.con = nullptr;
   R.jar = R.jv = R.force = nullptr; R.ncon = 0;
-  hessian_solve32(R, A, A, nullptr, ld, xs, lane, work, work, sync);
+  hessian_solve_any<TILE>(R, A, A, nullptr, ld, xs, lane, work, work, sync);
 }
 
 // ----------------------------------------------------------------------------- S1: kinematics + inertias + dof axes
 // One pass over the tree levels: body frames, spatial inertia about the tree's reference point
 // (the root body's origin) and the motion axis of every dof [upstream mj_kinematics + mj_comPos;
 // MuJoCo uses the subtree COM as reference point, any common point gives the same dynamics].
+//
+// fp32 note.  Spatial quantities about a far reference point are fine for the bias forces, but the
+// joint-space inertia of a light distal link is a difference of terms ~ m d^2 (d = distance to the
+// reference point, ~0.7 m for the gripper) that are 300x larger than the result.  The mass matrix is
+// therefore built from LOCAL quantities that never see world-magnitude offsets: every body keeps its inertia
+// about its own COM with the COM relative to its own origin (crb, COM form), its origin relative to the
+// parent's origin (dpos, accumulated from the local joint displacements) and the anchor of each hinge
+// relative to the body origin (danchor); see crb_mass_matrix.
 __device__ __forceinline__ void kinematics(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
   float *xpos = S + o.xpos, *xquat = S + o.xquat, *xmat = S + o.xmat, *cinert = S + o.cinert, *cdof = S + o.cdof;
+  float *crb = S + o.crb, *dpos = S + o.dpos, *danchor = S + o.danchor;
   const float* qpos = S + o.qpos;
   if (lane == 0) {
     xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
     for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? 1.f : 0.f;
-    for (int k = 0; k < 10; k++) cinert[k] = 0;
+    for (int k = 0; k < 10; k++) { cinert[k] = 0; crb[k] = 0; }
+    dpos[0] = dpos[1] = dpos[2] = 0;
   }
   __syncwarp();
   for (int lv = 0; lv < m.nlevel; lv++) {
     for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
       int b = PKI(lvl_body)[idx], p = PKI(body_parentid)[b], jn = PKI(body_jntnum)[b], ja = PKI(body_jntadr)[b];
       int rb = PKI(root_list)[PKI(body_rootidx)[b]];
-      float pos[3], q[4], ref[3];
+      float pos[3], q[4], ref[3], d[3];   // d = pos - parent origin, accumulated from local displacements only
       bool isfree = (jn == 1 && PKI(jnt_type)[ja] == JNT_FREE);
       if (isfree) {
         int qa = PKI(jnt_qposadr)[ja];
         pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
         q[0] = qpos[qa + 3]; q[1] = qpos[qa + 4]; q[2] = qpos[qa + 5]; q[3] = qpos[qa + 6];
         quat_normalize(q);
+        d[0] = pos[0]; d[1] = pos[1]; d[2] = pos[2];
       } else {
         const float *bq = PKF(body_quat) + 4 * b, *bp = PKF(body_pos) + 3 * b;
-        float t[3];
-        mat_vec(t, xmat + 9 * p, bp);
-        pos[0] = xpos[3 * p] + t[0]; pos[1] = xpos[3 * p + 1] + t[1]; pos[2] = xpos[3 * p + 2] + t[2];
+        mat_vec(d, xmat + 9 * p, bp);
+        pos[0] = xpos[3 * p] + d[0]; pos[1] = xpos[3 * p + 1] + d[1]; pos[2] = xpos[3 * p + 2] + d[2];
         quat_mul(q, xquat + 4 * p, bq);
       }
       if (lv == 0) { ref[0] = pos[0]; ref[1] = pos[1]; ref[2] = pos[2]; }
@@ -596,6 +666,7 @@ __device__ __forceinline__ void kinematics(const DevModel& m, float* S, int lane
           float* cr = cdof + 6 * (da + 3 + k);
           cr[0] = a3[0]; cr[1] = a3[1]; cr[2] = a3[2];
           cross3(cr + 3, a3, off);
+          for (int t = 0; t < 3; t++) { danchor[3 * (da + k) + t] = 0; danchor[3 * (da + 3 + k) + t] = 0; }
         }
       } else {
         for (int j = ja; j < ja + jn; j++) {
@@ -604,35 +675,44 @@ __device__ __forceinline__ void kinematics(const DevModel& m, float* S, int lane
           quat2mat(R, q);
           mat_vec(r, R, jp); anchor[0] = pos[0] + r[0]; anchor[1] = pos[1] + r[1]; anchor[2] = pos[2] + r[2];
           mat_vec(axis, R, jax);
-          int qa = PKI(jnt_qposadr)[j];
+          int qa = PKI(jnt_qposadr)[j], dj = PKI(jnt_dofadr)[j];
           float dq = qpos[qa] - PKF(qpos0)[qa];
-          float* c = cdof + 6 * PKI(jnt_dofadr)[j];
+          float* c = cdof + 6 * dj;
+          // anchor relative to the parent origin for now; made relative to the final body origin below
+          danchor[3 * dj] = d[0] + r[0]; danchor[3 * dj + 1] = d[1] + r[1]; danchor[3 * dj + 2] = d[2] + r[2];
           if (PKI(jnt_type)[j] == JNT_SLIDE) {
             pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+            d[0] += axis[0] * dq; d[1] += axis[1] * dq; d[2] += axis[2] * dq;
             c[0] = c[1] = c[2] = 0; c[3] = axis[0]; c[4] = axis[1]; c[5] = axis[2];
           } else {
             float sn, cs;
             sincosf(0.5f * dq, &sn, &cs);
-            float qr[4] = {cs, jax[0] * sn, jax[1] * sn, jax[2] * sn}, qn[4];
+            float qr[4] = {cs, jax[0] * sn, jax[1] * sn, jax[2] * sn}, qn[4], r2[3];
             quat_mul(qn, q, qr);
             q[0] = qn[0]; q[1] = qn[1]; q[2] = qn[2]; q[3] = qn[3];
             quat2mat(R, q);
-            mat_vec(r, R, jp);
-            pos[0] = anchor[0] - r[0]; pos[1] = anchor[1] - r[1]; pos[2] = anchor[2] - r[2];
+            mat_vec(r2, R, jp);
+            pos[0] = anchor[0] - r2[0]; pos[1] = anchor[1] - r2[1]; pos[2] = anchor[2] - r2[2];
+            d[0] += r[0] - r2[0]; d[1] += r[1] - r2[1]; d[2] += r[2] - r2[2];
             float off[3] = {ref[0] - anchor[0], ref[1] - anchor[1], ref[2] - anchor[2]};
             c[0] = axis[0]; c[1] = axis[1]; c[2] = axis[2];
             cross3(c + 3, axis, off);
           }
         }
+        for (int j = ja; j < ja + jn; j++) {
+          int dj = PKI(jnt_dofadr)[j];
+          danchor[3 * dj] -= d[0]; danchor[3 * dj + 1] -= d[1]; danchor[3 * dj + 2] -= d[2];
+        }
         quat_normalize(q);
       }
       xpos[3 * b] = pos[0]; xpos[3 * b + 1] = pos[1]; xpos[3 * b + 2] = pos[2];
       xquat[4 * b] = q[0]; xquat[4 * b + 1] = q[1]; xquat[4 * b + 2] = q[2]; xquat[4 * b + 3] = q[3];
+      dpos[3 * b] = d[0]; dpos[3 * b + 1] = d[1]; dpos[3 * b + 2] = d[2];
       float R[9], t[3], qi[4];
       quat2mat(R, q);
 #pragma unroll
       for (int k = 0; k < 9; k++) xmat[9 * b + k] = R[k];
-      // spatial inertia about the reference point, world axes
+      // spatial inertia about the reference point, world axes (cinert) and about the body's own COM (crb, COM form)
       mat_vec(t, R, PKF(body_ipos) + 3 * b);
       float off[3] = {pos[0] + t[0] - ref[0], pos[1] + t[1] - ref[1], pos[2] + t[2] - ref[2]};
       quat_mul(qi, q, PKF(body_iquat) + 4 * b);
@@ -640,52 +720,96 @@ __device__ __forceinline__ void kinematics(const DevModel& m, float* S, int lane
       float I0 = PKF(body_inertia)[3 * b], I1 = PKF(body_inertia)[3 * b + 1], I2 = PKF(body_inertia)[3 * b + 2];
       float mass = PKF(body_mass)[b], o2 = dot3(off, off);
       float* ci = cinert + 10 * b;
+      float* cb = crb + 10 * b;
 #define IW(r, c) (R[3 * r] * I0 * R[3 * c] + R[3 * r + 1] * I1 * R[3 * c + 1] + R[3 * r + 2] * I2 * R[3 * c + 2])
-      ci[0] = IW(0, 0) + mass * (o2 - off[0] * off[0]);
-      ci[1] = IW(1, 1) + mass * (o2 - off[1] * off[1]);
-      ci[2] = IW(2, 2) + mass * (o2 - off[2] * off[2]);
-      ci[3] = IW(0, 1) - mass * off[0] * off[1];
-      ci[4] = IW(0, 2) - mass * off[0] * off[2];
-      ci[5] = IW(1, 2) - mass * off[1] * off[2];
+      cb[0] = IW(0, 0); cb[1] = IW(1, 1); cb[2] = IW(2, 2); cb[3] = IW(0, 1); cb[4] = IW(0, 2); cb[5] = IW(1, 2);
 #undef IW
+      cb[6] = t[0]; cb[7] = t[1]; cb[8] = t[2]; cb[9] = mass;
+      ci[0] = cb[0] + mass * (o2 - off[0] * off[0]);
+      ci[1] = cb[1] + mass * (o2 - off[1] * off[1]);
+      ci[2] = cb[2] + mass * (o2 - off[2] * off[2]);
+      ci[3] = cb[3] - mass * off[0] * off[1];
+      ci[4] = cb[4] - mass * off[0] * off[2];
+      ci[5] = cb[5] - mass * off[1] * off[2];
       ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2]; ci[9] = mass;
     }
     __syncwarp();
   }
 }
 
-// composite inertia (children gathered level by level) and the dense joint-space inertia M
+// Composite rigid bodies in COM form -- crb[b] = {inertia about the composite's COM (xx yy zz xy xz yz, world axes),
+// COM relative to body b's origin, mass} -- gathered level by level from the leaves, and the dense joint-space
+// inertia  M_ij = w_i . Ic w_j + mass v_i . v_j  (j = i or an ancestor dof of i; w, v = angular velocity and
+// velocity of the composite's COM per unit rate of the dof).  All lever arms are sums of local offsets.
 __device__ __forceinline__ void crb_mass_matrix(const DevModel& m, float* S, int lane) {
   const EnvLayout& o = m.L;
-  const float *cinert = S + o.cinert, *cdof = S + o.cdof;
+  const float *cdof = S + o.cdof, *dpos = S + o.dpos, *danchor = S + o.danchor;
   float *crb = S + o.crb, *M = S + o.M;
   int nv = m.nv;
   _Pragma("unroll 1") for (int k = lane; k < nv * o.ldm; k += 32) M[k] = 0;
   for (int lv = m.nlevel - 1; lv >= 0; lv--) {
     for (int idx = PKI(lvl_adr)[lv] + lane; idx < PKI(lvl_adr)[lv + 1]; idx += 32) {
       int b = PKI(lvl_body)[idx];
-      float acc[10];
-#pragma unroll
-      for (int k = 0; k < 10; k++) acc[k] = cinert[10 * b + k];
-      for (int c = PKI(child_adr)[b]; c < PKI(child_adr)[b + 1]; c++) {
-        const float* cc = crb + 10 * PKI(child_list)[c];
-#pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] += cc[k];
+      int c0 = PKI(child_adr)[b], c1 = PKI(child_adr)[b + 1];
+      if (c0 == c1) continue;
+      float* cb = crb + 10 * b;
+      // total mass and COM (relative to b's origin)
+      float mass = cb[9], mc[3] = {mass * cb[6], mass * cb[7], mass * cb[8]};
+      for (int c = c0; c < c1; c++) {
+        int ch = PKI(child_list)[c];
+        const float* cc = crb + 10 * ch;
+        float mk = cc[9];
+        mass += mk;
+        for (int t = 0; t < 3; t++) mc[t] += mk * (dpos[3 * ch + t] + cc[6 + t]);
+      }
+      float inv = mass > 0 ? 1.0f / mass : 0.f, com[3] = {mc[0] * inv, mc[1] * inv, mc[2] * inv};
+      // inertia about the new COM: parallel-axis shift of every part by its own (local) offset
+      float I[6];
+      {
+        float dd[3] = {cb[6] - com[0], cb[7] - com[1], cb[8] - com[2]}, mk = cb[9], d2 = dot3(dd, dd);
+        I[0] = cb[0] + mk * (d2 - dd[0] * dd[0]); I[1] = cb[1] + mk * (d2 - dd[1] * dd[1]); I[2] = cb[2] + mk * (d2 - dd[2] * dd[2]);
+        I[3] = cb[3] - mk * dd[0] * dd[1]; I[4] = cb[4] - mk * dd[0] * dd[2]; I[5] = cb[5] - mk * dd[1] * dd[2];
+      }
+      for (int c = c0; c < c1; c++) {
+        int ch = PKI(child_list)[c];
+        const float* cc = crb + 10 * ch;
+        float dd[3] = {dpos[3 * ch] + cc[6] - com[0], dpos[3 * ch + 1] + cc[7] - com[1], dpos[3 * ch + 2] + cc[8] - com[2]};
+        float mk = cc[9], d2 = dot3(dd, dd);
+        I[0] += cc[0] + mk * (d2 - dd[0] * dd[0]); I[1] += cc[1] + mk * (d2 - dd[1] * dd[1]); I[2] += cc[2] + mk * (d2 - dd[2] * dd[2]);
+        I[3] += cc[3] - mk * dd[0] * dd[1]; I[4] += cc[4] - mk * dd[0] * dd[2]; I[5] += cc[5] - mk * dd[1] * dd[2];
       }
 #pragma unroll
-      for (int k = 0; k < 10; k++) crb[10 * b + k] = acc[k];
+      for (int k = 0; k < 6; k++) cb[k] = I[k];
+      cb[6] = com[0]; cb[7] = com[1]; cb[8] = com[2]; cb[9] = mass;
     }
     __syncwarp();
   }
   _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
-    float buf[6];
-    mul_inert_vec(buf, crb + 10 * PKI(dof_bodyid)[i], cdof + 6 * i);
+    int cur = PKI(dof_bodyid)[i];
+    const float* cb = crb + 10 * cur;
+    const float I[6] = {cb[0], cb[1], cb[2], cb[3], cb[4], cb[5]}, mass = cb[9];
+    float c[3] = {cb[6], cb[7], cb[8]};   // composite COM relative to the origin of body `cur`
+    float Iw[3] = {0, 0, 0}, mv[3] = {0, 0, 0};
     for (int j = i; j >= 0; j = PKI(dof_parentid)[j]) {
-      const float* c = cdof + 6 * j;
-      float v = c[0] * buf[0] + c[1] * buf[1] + c[2] * buf[2] + c[3] * buf[3] + c[4] * buf[4] + c[5] * buf[5];
-      if (j == i) v += PKF(dof_armature)[i];
-      M[i * o.ldm + j] = v;
-      M[j * o.ldm + i] = v;
+      int bj = PKI(dof_bodyid)[j];
+      while (cur != bj) { c[0] += dpos[3 * cur]; c[1] += dpos[3 * cur + 1]; c[2] += dpos[3 * cur + 2]; cur = PKI(body_parentid)[cur]; }
+      const float* cd = cdof + 6 * j;
+      float w[3] = {cd[0], cd[1], cd[2]}, v[3];
+      if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f) { v[0] = cd[3]; v[1] = cd[4]; v[2] = cd[5]; }   // slide / free translation: the axis
+      else {
+        float arm[3] = {c[0] - danchor[3 * j], c[1] - danchor[3 * j + 1], c[2] - danchor[3 * j + 2]};
+        cross3(v, w, arm);
+      }
+      if (j == i) {
+        Iw[0] = I[0] * w[0] + I[3] * w[1] + I[4] * w[2];
+        Iw[1] = I[3] * w[0] + I[1] * w[1] + I[5] * w[2];
+        Iw[2] = I[4] * w[0] + I[5] * w[1] + I[2] * w[2];
+        mv[0] = mass * v[0]; mv[1] = mass * v[1]; mv[2] = mass * v[2];
+      }
+      float val = dot3(w, Iw) + dot3(v, mv);
+      if (j == i) val += PKF(dof_armature)[i];
+      M[i * o.ldm + j] = val;
+      M[j * o.ldm + i] = val;
     }
   }
   __syncwarp();
@@ -1640,6 +1764,7 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, co
 // Every warp of the CTA makes this call (`active` = it owns an env).  With `sync` the Newton loop is
 // CTA-uniform: the warps meet before the gradient, the Hessian and the line search of every iteration
 // (converged warps only keep the barriers company), which lets them share instruction-cache lines.
+template <int TILE>
 __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, int ns, int nefc, int ncon, int lane, bool active, int sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv;
@@ -1685,26 +1810,29 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
     cost = eval_constraints<true>(R, 0.f, lane).x;
   }
   }
-  int iter = 0;
+  int iter = 0, nunres = 0;
+  bool unresolved = false;
   while (true) {
     if (!sync && done) break;
     if (!done) {
       mul_JT(R, qfc, force, lane);
-      float g2 = 0;
-      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) { float gi = Ma[i] - qs[i] - qfc[i]; grad[i] = gi; search[i] = -gi; g2 += gi * gi; }
-      g2 = warp_sum(g2);
+      float g2 = 0, dec = 0;
+      _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
+        float gi = Ma[i] - qs[i] - qfc[i];
+        grad[i] = gi; search[i] = -gi; g2 += gi * gi; dec += gi * gi / M[i * o.ldm + i];
+      }
+      g2 = warp_sum(g2); dec = warp_sum(dec);
       __syncwarp();
       if (iter >= m.iterations) done = true;
       else if (iter > 0 && scale * sqrtf(g2) < m.tolerance) done = true;
+      // fp32: the last step's improvement was below the resolution of the cost.  The cost is blind to light dofs
+      // (a 1e-6 kg m^2 finger tip at 100 rad/s^2 is 5e-3 of a cost of 1e4), the inertia-scaled gradient is not:
+      // stop only when 0.5 g^T diag(M)^-1 g (>= the Newton decrement's order) is below the tolerance as well
+      else if (unresolved && (scale * 0.5f * dec < m.tolerance || ++nunres > 3)) done = true;
     }
-    if (nv <= 32) {
-      // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
-      // every warp whether any warp of the CTA is still iterating
-      if (!hessian_solve32(R, S + o.H, M, S + o.tmpJ, o.ldm, search, lane, !done, !done, sync)) break;
-    } else {
-      if (sync && !group_sync_or(sync, !done)) break;
-      if (!done) { build_hessian(R, S + o.H, M, S + o.tmpJ, o.ldm, lane); chol_solve(S + o.H, search, nv, o.ldm, lane); }
-    }
+    // the one CTA-wide barrier of the iteration sits in front of the factorisation; it also tells
+    // every warp whether any warp of the CTA is still iterating
+    if (!hessian_solve_any<TILE>(R, S + o.H, M, S + o.tmpJ, o.ldm, search, lane, !done, !done, sync)) break;
     if (done) continue;
     // expected decrease 0.5 * |grad . search| below tolerance: converged (well conditioned in fp32)
     float gs = 0, ss = 0;
@@ -1750,8 +1878,9 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
       cost += warp_sum(gsum);
     }
     iter++;
-    // improvement below the solver tolerance, or below what fp32 can resolve in the cost: stop
-    if (oldcost - cost < fmaxf(m.tolerance / scale, 2e-7f * fabsf(cost))) {
+    // improvement below the solver tolerance: stop; below what fp32 can resolve in the cost: let the gradient decide
+    unresolved = oldcost - cost < 2e-7f * fabsf(cost);
+    if (!unresolved && oldcost - cost < m.tolerance / scale) {
       mul_JT(R, qfc, force, lane);
       done = true;
     }
@@ -1760,6 +1889,7 @@ __device__ __forceinline__ int solve_constraints(const DevModel& m, float* S, in
 }
 
 // ----------------------------------------------------------------------------- S9: implicitfast + advance
+template <int TILE>
 __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane, bool active, int sync) {
   const EnvLayout& o = m.L;
   int nv = m.nv, ld = o.ldm;
@@ -1785,8 +1915,7 @@ __device__ __forceinline__ void integrate(const DevModel& m, float* S, int lane,
     rhs[i] = S[o.qfrc_smooth + i] + S[o.qfrc_con + i];
   }
   __syncwarp();
-  if (nv <= 32) chol_solve32(A, nv, ld, rhs, lane, active, sync);
-  else if (active) { chol_factor(A, nv, ld, lane); chol_solve(A, rhs, nv, ld, lane); }
+  chol_solve_any<TILE>(A, nv, ld, rhs, lane, active, sync);
   if (!active) return;
   _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) qvel[i] += h * rhs[i];
   __syncwarp();
@@ -2039,7 +2168,8 @@ __device__ __forceinline__ void gather_contacts(const DevModel& m, const StepArg
 // own envs of similar cost and meet at one barrier per Newton iteration (they then stream the long
 // straight-line factorisation through the instruction cache together).  Otherwise every warp fetches its
 // own env and runs free.
-extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevModel m, const StepArgs a) {
+template <int TILE>
+__global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevModel m, const StepArgs a) {
   const EnvLayout& o = m.L;
   load_pack(m.pack, m.pk.nwords3);   // part 1 of the pack only; pair_cg (part 2) is read from global memory (GPI)
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -2082,9 +2212,8 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
     // qacc_smooth = M^-1 qfrc_smooth (factor lives in the H buffer until the solver rebuilds it)
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.qacc_smooth + i] = S[o.qfrc_smooth + i];
     copy_matrix(S + o.H, S + o.M, m.nv, o.ldm, lane);
-    if (m.nv <= 32) chol_solve32(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, true, bar);
-    else { chol_factor(S + o.H, m.nv, o.ldm, lane); chol_solve(S + o.H, S + o.qacc_smooth, m.nv, o.ldm, lane); }
-    fi.iter = solve_constraints(m, S, fi.ns, fi.nefc, fi.ncon, lane, true, bar);
+    chol_solve_any<TILE>(S + o.H, m.nv, o.ldm, S + o.qacc_smooth, lane, true, bar);
+    fi.iter = solve_constraints<TILE>(m, S, fi.ns, fi.nefc, fi.ncon, lane, true, bar);
     int cost = a.cost_w * fi.iter + fi.nnarrow;   // this step's cost: the predictor for the next launch's schedule
     _Pragma("unroll 1") for (int i = lane; i < m.nv; i += 32) S[o.warm + i] = S[o.qacc + i];
     __syncwarp();
@@ -2124,7 +2253,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
       __syncwarp();
     }
     if (!a.forward_only) {
-      if (!bad || lock) integrate(m, S, lane, !bad, bar);
+      if (!bad || lock) integrate<TILE>(m, S, lane, !bad, bar);
       time += m.timestep;
       if (active) {
         _Pragma("unroll 1") for (int i = lane; i < m.nq; i += 32) a.qpos[(size_t)env * m.nq + i] = S[o.qpos + i];
@@ -2136,4 +2265,24 @@ extern "C" __global__ void __launch_bounds__(256, 1) ss_solve_kernel(const DevMo
     if (a.env_flags && lane == 0 && active) a.env_flags[env] = flags;
     __syncwarp();
   }
+}
+
+// ---- host side: the solve kernel is instantiated per register tile; api.cu picks one by the model's nv -----------
+int ss_solve_tile(int nv) { return nv <= 28 ? 28 : nv <= 32 ? 32 : nv <= 40 ? 40 : nv <= 44 ? 44 : nv <= 48 ? 48 : 64; }
+#define SS_TILE_DISPATCH(tile, expr)                  \
+  switch (tile) {                                     \
+    case 28: { constexpr int T = 28; expr; } break;   \
+    case 32: { constexpr int T = 32; expr; } break;   \
+    case 40: { constexpr int T = 40; expr; } break;   \
+    case 44: { constexpr int T = 44; expr; } break;   \
+    case 48: { constexpr int T = 48; expr; } break;   \
+    default: { constexpr int T = 64; expr; } break;   \
+  }
+cudaError_t ss_solve_set_smem(int tile, int bytes) {
+  cudaError_t e = cudaSuccess;
+  SS_TILE_DISPATCH(tile, e = cudaFuncSetAttribute(ss_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return e;
+}
+void ss_solve_launch(int tile, int grid, int block, size_t smem, cudaStream_t st, const DevModel& m, const StepArgs& a) {
+  SS_TILE_DISPATCH(tile, (ss_solve_kernel<T><<<grid, block, smem, st>>>(m, a)));
 }
