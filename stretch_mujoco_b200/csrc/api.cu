@@ -476,6 +476,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
     ss_batch_free(B);
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  if (const char* e = getenv("SS_RENDER")) B->render_mode = strcmp(e, "raycast") == 0 ? 0 : 1;   // A/B knob: the ray-cast camera path
   B->nosort = getenv("SS_NOSORT") != nullptr;
   // schedule key: bucket = min(255, cost_scale * cost), cost = cost_w x Newton iterations + narrowphase queries
   // (47.3 ms per 50 steps for 16 / x1 against 47.9 ms for 8 / x4)
@@ -499,6 +500,12 @@ extern "C" void ss_batch_free(ss_batch* B) {
   if (!B) return;
   cudaSetDevice(B->model->device);
   if (B->ray_xf) cudaFree(B->ray_xf);
+  if (B->zbuf) cudaFree(B->zbuf);
+  if (B->rs_cam) cudaFree(B->rs_cam);
+  if (B->rs_prim) cudaFree(B->rs_prim);
+  if (B->rs_cvis) cudaFree(B->rs_cvis);
+  if (B->rs_queue) cudaFree(B->rs_queue);
+  if (B->rs_qcount) cudaFree(B->rs_qcount);
   if (B->pb) cudaFree(B->pb);
   if (B->rec) cudaFree(B->rec);
   if (B->npass) cudaFree(B->npass);

@@ -48,6 +48,17 @@ struct ss_batch {
   StatusIds ids = {};
   bool ids_valid = false;
   float* ray_xf = nullptr;  // [nenv, nraygeom, 12] world transforms of ray-visible geoms (library-owned scratch)
+  // raster camera path (library-owned scratch, sized for one sub-chunk of envs)
+  int render_mode = 1;                       // 1 = rasterised meshes + analytic primitives, 0 = ray casting (SS_RENDER=raycast)
+  unsigned long long* zbuf = nullptr;        // [nsub, H, W] depth | triangle keys
+  size_t zbuf_cap = 0;                       // entries
+  float* rs_cam = nullptr;                   // [nsub, 16] eye, rotation, focal
+  int* rs_prim = nullptr;                    // [nsub, 1 + MAXPRIM] camera-visible primitive geoms inside the image pyramid
+  unsigned char* rs_cvis = nullptr;          // [nsub, nchunk] chunk inside the image pyramid?
+  void* rs_queue = nullptr;                  // [rs_qcap] (triangle, row band) items with pixel boxes too large for their owner thread
+  int* rs_qcount = nullptr;
+  int rs_qcap = 0;
+  int rs_nsub = 0;
 };
 
 int ss_fail(const char* fmt, ...);

@@ -20,6 +20,11 @@ struct RayModel {
   const float* range_cutoff;
   int nrange;
   float headlight[9], sky[6];
+  // raster camera path: work chunks of <= RCHUNK consecutive triangles (BVH leaf order, spatially compact) of the
+  // camera-visible mesh geoms: (ray-geom index, first triangle, count, 0) and the chunk's bounds in the mesh frame
+  int nchunk;
+  const int4* rchunk;
+  const float4* rchunk_box;   // 2 per chunk: lo, hi
   const int *light_bodyid, *light_directional;
   const float *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;
 };
