@@ -47,14 +47,14 @@ NAV = ("nav_camera_rgb", 800, 600, 102.0, 0.0, True, False)
 CONFIGS = {
     "cfg2": dict(blob="stretch_empty_floor.ssm", mj_steps=50, cams=[], lidar=False, maxcon=32,
                  workload="cfg2: {n} parallel Stretch envs per GPU, empty-floor scene, physics only (no sensors)"),
-    "default": dict(blob="stretch_default_scene.ssm", mj_steps=50, cams=[], lidar=False, maxcon=64,
+    "default": dict(blob="stretch_default_scene.ssm", mj_steps=50, cams=[], lidar=False, maxcon=72, maxefc=288,
                     workload="default scene.xml (dock, table, two free objects; nv = 44): {n} envs per GPU, physics only"),
     "cfg3": dict(blob="stretch_empty_floor_render.ssm.z", mj_steps=5, cams=[HEAD640], lidar=False, maxcon=32,
                  workload="cfg3: {n} envs per GPU, empty floor, physics + 640x480 head RGB+depth render after every mj_step"),
-    "cfg4": dict(blob="stretch_kitchen_proxy_render.ssm.z", mj_steps=5, cams=[HEAD, WRIST], lidar=True, maxcon=32,
+    "cfg4": dict(blob="stretch_kitchen_proxy_render.ssm.z", mj_steps=5, cams=[HEAD, WRIST], lidar=True, maxcon=40,
                  workload="cfg4: {n} envs per GPU, kitchen proxy (Robocasa assets are download-only), physics + 1000-ray lidar "
                           "+ head 424x240 + wrist 480x270 RGB+depth after every mj_step"),
-    "cfg5": dict(blob="stretch_kitchen_proxy_render.ssm.z", mj_steps=5, cams=[HEAD, WRIST, NAV], lidar=True, maxcon=32,
+    "cfg5": dict(blob="stretch_kitchen_proxy_render.ssm.z", mj_steps=5, cams=[HEAD, WRIST, NAV], lidar=True, maxcon=40,
                  workload="cfg5: {n} envs per GPU, kitchen proxy, physics + 1000-ray lidar + all five cameras "
                           "(head / wrist RGB+depth, nav 800x600 RGB) after every mj_step"),
 }
@@ -258,7 +258,7 @@ def run_ours(args, cfg):
     else:
         nenv = args.nenv
         env0 = rank * nenv
-    sim = StretchMujocoSimulator(model_blob=raw, nenv=nenv, device=local, maxcon=cfg["maxcon"])
+    sim = StretchMujocoSimulator(model_blob=raw, nenv=nenv, device=local, maxcon=cfg["maxcon"], maxefc=cfg.get("maxefc", 0))
     sim.start(home=False)
     B = sim.batch
     dm = sim.dmodel
@@ -394,6 +394,17 @@ def run_ours(args, cfg):
             dist.all_reduce(t3, op=dist.ReduceOp.MAX)
         per_step = world * nenv * nst / (float(t3.item()) * 1e-3)
 
+    # ---- leg 4: per-kernel durations of the physics pipeline (CUDA events inside the library, kernels serialised on one stream)
+    kms = None
+    if hasattr(B, "profile_step"):
+        acc = np.zeros(3)
+        nprof = 50
+        for _ in range(5):
+            B.profile_step()
+        for _ in range(nprof):
+            acc += np.array(B.profile_step())
+        kms = acc / nprof
+
     # ---- end-of-rollout metrics: the path's only collective
     metrics = torch.stack([torch.tensor(float(nenv * S * K), device=dev), torch.tensor(total_ms, device=dev, dtype=torch.float32),
                            qsum_leg1, ncon_leg1, (flags_leg1 & 1).ne(0).sum().float(), (flags_leg1 & 2).ne(0).sum().float()]).float()
@@ -427,12 +438,23 @@ def run_ours(args, cfg):
     else:
         algo = ALGO_BYTES_PER_ENV_STEP * nenv * S
         kernel = "ss_solve_kernel"
-        note = ("per bench step (= launches_per_step launches: schedule + ss_smooth + ss_narrow + ss_solve per mj_step and env set); physics is "
-                "instruction-issue / latency bound, not HBM bound: 828 algorithmic B per env-step (SURVEY.md 8(d)); the binding figures "
-                "are issue_slot_util and lane_util (ncu, profiles/physics_r2.json)")
+        note = ("achieved = 828 algorithmic B per env-step (SURVEY.md 8(d)) x envs / mean duration of one ss_solve_kernel launch over all envs, "
+                "measured with CUDA events inside the library (ss_batch_profile_step, kernels serialised); step_frac_of_roofline is the same "
+                "figure for the whole bench step (launches_per_step launches: schedule + ss_smooth + ss_narrow + ss_solve per mj_step and env "
+                "set, overlapped on three streams).  Physics is instruction-issue / latency bound, not HBM bound: the binding figures are "
+                "issue_slot_util and lane_util (ncu capture of the same kernels, profiles/physics_r2.json)")
     achieved = algo / (step_ms * 1e-3) / 1e9
+    kernel_ms = step_ms
+    if kms is not None and not cams and scan is None:
+        # the dominant kernel alone: its mean launch duration over 50 serialised mj_steps of all envs, against the
+        # 828 algorithmic bytes of an env-step (the whole step's state traffic is attributed to it)
+        kernel_ms = float(kms[2])
+        achieved = ALGO_BYTES_PER_ENV_STEP * nenv / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof.get(args.config, {}).get("dram_bytes_per_bench_step"), "kernel": kernel, "kernel_ms": step_ms,
+                "traffic": prof.get(args.config, {}).get("dram_bytes_per_launch"), "kernel": kernel, "kernel_ms": kernel_ms,
+                "kernels_ms_per_mj_step": None if kms is None else {"ss_smooth_kernel": float(kms[0]), "ss_narrow_kernel": float(kms[1]),
+                                                                    "ss_solve_kernel": float(kms[2]), "note": "serialised, one env set"},
+                "step_frac_of_roofline": algo / (step_ms * 1e-3) / 1e9 / peak,
                 "algorithmic_bytes_per_step": algo, "launches_per_step": int(launches) // K,
                 "issue_slot_util": prof.get("issue_slot_util"), "lane_util": prof.get("lane_util"),
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "note": note}

@@ -88,6 +88,10 @@ int ss_batch_reset(ss_batch*, const int32_t* env_mask_dev, int key_id, ss_stream
 int ss_batch_step(ss_batch*, int nsteps, ss_stream);
 /* forward dynamics only (mj_forward): fills the output buffers, leaves the state untouched */
 int ss_batch_forward(ss_batch*, ss_stream);
+/* measurement aid: one mj_step whose three kernels (smooth dynamics + broadphase, narrowphase, constraints + solver +
+ * integration) run back to back on the caller's stream with CUDA events between them; ms3 (HOST) receives their
+ * durations.  Advances the state like ss_batch_step(1); the only call that synchronises (on its own last event). */
+int ss_batch_profile_step(ss_batch*, float* ms3, ss_stream);
 /* number of kernels launched by this batch since creation (bench.py "gpu_launches") */
 long ss_batch_launch_count(const ss_batch*);
 

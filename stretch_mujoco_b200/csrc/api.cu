@@ -125,10 +125,10 @@ static int build_layout(DevModel& m, int kernel) {
     o.qacc = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
     o.con = take(m.maxcon * CON_STRIDE);
     o.s_d1 = take(m.maxsimple); o.s_c1 = take(m.maxsimple); o.s_d2 = take(m.maxsimple); o.s_c2 = take(m.maxsimple);
-    o.e_R = take(m.maxrow); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxsimple); o.e_info = take(m.maxrow);   // friction loss: simple rows only
-    o.J = take(std::max(m.maxcrow * o.ldj, nb * 6));
+    o.e_R = take(m.maxsimple); o.e_D = take(m.maxrow); o.e_aref = take(m.maxrow); o.e_floss = take(m.maxsimple); o.e_info = take(m.maxrow);   // R, friction loss: simple rows only
+    o.J = take(std::max(m.maxjnz, nb * 6));
     o.cacc = o.J;                        // the IMU pass rebuilds body accelerations after the solve, when J is dead
-    o.H = take(nv * o.ldm); o.tmpJ = take(2 * o.ldj);   // the register-tile Hessian build stages two vectors per cone block
+    o.H = take(nv * o.ldm); o.tmpJ = take(3 * o.ldj);   // dense scratch rows of the Hessian build: two cone vectors + one expanded Jacobian row
     o.e_force = take(m.maxrow); o.e_jar = take(m.maxrow); o.e_jv = take(m.maxrow);
     o.v_Ma = take(nv); o.v_grad = take(nv); o.v_search = take(nv); o.v_mv = take(nv); o.v_tmp = take(nv);
   }
@@ -430,8 +430,13 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   m.maxcon = maxcon > 0 ? maxcon : 32;
   int nsimple = m.neq + m.nfloss + 2 * m.nlimited;
   m.maxsimple = nsimple;
-  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 96;
+  m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 160;
   m.maxrow = m.maxsimple + m.maxcrow;
+  // packed contact Jacobian: a row holds only the dofs between the two bodies' chains (wheel on floor: 7, wrist on base: ~10, free
+  // object on table: 6), 12 floats per row of capacity cover the measured workloads (an overflow drops the contact and
+  // sets env_flags bit 1, like the row capacity), but any single contact (6 rows of nv) must fit
+  m.maxjnz = std::max(m.maxcrow * 12, 6 * ((m.nv + 3) & ~3));
+  if (const char* e = getenv("SS_MAXJNZ")) m.maxjnz = std::max(m.maxjnz / 4, atoi(e));
   B->dm1 = m;
   B->smem_per_env = (size_t)build_layout(m, 3) * sizeof(float);
   B->smem_per_env1 = (size_t)build_layout(B->dm1, 1) * sizeof(float);
@@ -461,7 +466,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   B->grid1 = std::min((nenv + wpb1 - 1) / wpb1, sms);
   B->grid2 = 2 * sms;
   // pipeline scratch: persistent blocks, broadphase slots, narrowphase records, work-item queue
-  B->maxslot = std::max(32, 2 * m.maxcon);
+  B->maxslot = std::max(32, 3 * m.maxcon);   // broadphase candidates per env (global scratch only)
   if (const char* e = getenv("SS_MAXSLOT")) B->maxslot = std::max(8, atoi(e));
   size_t nslot = (size_t)nenv * B->maxslot;
   if (cudaMalloc((void**)&B->pb, sizeof(float) * (size_t)nenv * B->pb_stride) != cudaSuccess ||
@@ -529,7 +534,7 @@ extern "C" int ss_batch_set_debug(ss_batch* B, const ss_debug_buffers* d) {
   return 0;
 }
 
-static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream stream) {
+static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream stream, cudaEvent_t* marks = nullptr) {
   StepArgs a;
   memset(&a, 0, sizeof(a));
   const ss_buffers& f = B->bufs;
@@ -560,7 +565,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   // that the other set's tails leave idle.
   const int cost_scale = B->cost_scale;
   cudaStream_t user = (cudaStream_t)stream;
-  int nsets = (forward_only || nsteps < 2) ? 1 : B->nsets;
+  int nsets = (forward_only || nsteps < 2 || marks) ? 1 : B->nsets;
   if (nsets > 1) {
     CUDA_OK(cudaEventRecord(B->ev_fork, user));
     for (int k = 0; k < nsets; k++) CUDA_OK(cudaStreamWaitEvent(B->side[k], B->ev_fork, 0));
@@ -576,9 +581,13 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
       schedule_kernel<<<1, 1024, 0, st>>>(e0, a.nenv, B->cost, B->nosort ? -1 : 0, cost_scale, B->order + e0, a.work_counter);
       int g1 = std::min((a.nenv + B->warps_per_block1 - 1) / B->warps_per_block1, B->grid1);
       int g3 = std::min((a.nenv + B->warps_per_block - 1) / B->warps_per_block, B->grid);
+      if (marks) cudaEventRecord(marks[0], st);
       ss_smooth_kernel<<<g1, B->warps_per_block1 * 32, smem1, st>>>(B->dm1, a);
+      if (marks) cudaEventRecord(marks[1], st);
       ss_narrow_kernel<<<B->grid2, NARROW_THREADS, smem2, st>>>(B->dm1, a);
+      if (marks) cudaEventRecord(marks[2], st);
       ss_solve_launch(tile, g3, B->warps_per_block * 32, smem3, st, B->dm, a);
+      if (marks) cudaEventRecord(marks[3], st);
       B->launches += 4;
     }
   }
@@ -594,6 +603,21 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
 extern "C" int ss_batch_step(ss_batch* B, int nsteps, ss_stream stream) {
   if (!B || nsteps <= 0) return ss_fail("ss_batch_step: bad argument");
   return launch_physics(B, nsteps, 0, stream);
+}
+// One mj_step with its three kernels serialised on the caller's stream (one env set) and CUDA events between them:
+// per-kernel durations for the roofline line of bench.py.  The only entry point that synchronises (on its last event).
+extern "C" int ss_batch_profile_step(ss_batch* B, float* ms3, ss_stream stream) {
+  if (!B || !ms3) return ss_fail("ss_batch_profile_step: bad argument");
+  cudaSetDevice(B->model->device);
+  cudaEvent_t ev[4];
+  for (int k = 0; k < 4; k++) CUDA_OK(cudaEventCreate(&ev[k]));
+  int rc = launch_physics(B, 1, 0, stream, ev);
+  if (rc == 0) {
+    CUDA_OK(cudaEventSynchronize(ev[3]));
+    for (int k = 0; k < 3; k++) CUDA_OK(cudaEventElapsedTime(&ms3[k], ev[k], ev[k + 1]));
+  }
+  for (int k = 0; k < 4; k++) cudaEventDestroy(ev[k]);
+  return rc;
 }
 extern "C" int ss_batch_forward(ss_batch* B, ss_stream stream) {
   if (!B) return ss_fail("ss_batch_forward: null batch");

@@ -45,12 +45,12 @@ struct EnvLayout {
   int con;                                       // contacts [maxcon * CON_STRIDE]
   int s_d1, s_c1, s_d2, s_c2;                    // simple rows (equality, friction loss, limit): <=2 non-zeros
   int e_R, e_D, e_aref, e_floss, e_info;         // all rows [maxrow]; e_info packs type | state<<4 | id<<8
-  int J, ldj;                                    // dense Jacobian of CONTACT rows [maxcrow * ldj]
+  int J, ldj;                                    // packed Jacobian of the CONTACT rows [maxjnz] (C_JOFS / C_MASK*); ldj = nv rounded up to 4 (dense scratch rows)
   int H, tmpJ, e_force, e_jar, e_jv, v_Ma, v_grad, v_search, v_mv, v_tmp;
   int total;
 };
 
-#define CON_STRIDE 24
+#define CON_STRIDE 28
 // contact record fields (float slots); friction/solref/solimp are looked up through the pair id
 #define C_POS 0
 #define C_FRAME 3
@@ -62,6 +62,12 @@ struct EnvLayout {
 #define C_BODY1 17
 #define C_BODY2 18
 #define C_FRICTION 19   // friction[5]: tangent1, tangent2, torsional, rolling1, rolling2
+// packed Jacobian rows of the contact: the dofs on exactly one of the two bodies' chains (bit i of the 64-bit mask), values
+// in dof order, row stride C_JW (popcount rounded up to 4), first row at J + C_JOFS; C_CMASK: 4-column chunks with a dof
+#define C_MASKLO 24
+#define C_MASKHI 25
+#define C_JOFS 26
+#define C_CMASK 27
 
 // word offsets into the model pack
 struct PackOffsets {
@@ -85,7 +91,7 @@ struct PackOffsets {
 struct DevModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, ncam, ntendon, neq, nsensor, nsensordata, nkey, npair, nmesh;
   int nlevel, nroot, ncgeom, nfloss, nlimited, naccel;
-  int maxcon, maxcrow, maxsimple, maxrow;
+  int maxcon, maxcrow, maxsimple, maxrow, maxjnz;
   float timestep, gravity[3], impratio, tolerance, ls_tolerance, meaninertia, max_margin;
   int iterations, ls_iterations;
   EnvLayout L;

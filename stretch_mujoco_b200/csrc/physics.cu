@@ -155,16 +155,28 @@ __device__ __noinline__ void copy_matrix(float* dst, const float* src, int n, in
 }
 
 // ---- n <= 32: one matrix row per lane held in REGISTERS, columns exchanged by warp shuffles ------------
-// a += s * v[0..NT) (v in shared memory, 16-byte aligned)
+// a += s * v[0..NT) (v in shared memory, 16-byte aligned); cmask: the 4-column chunks of v that hold anything
 template <int NT>
-__device__ __forceinline__ void rank1_row(float (&a)[NT], float s, const float* v) {
+__device__ __forceinline__ void rank1_row(float (&a)[NT], float s, const float* v, unsigned cmask) {
   const float4* v4 = reinterpret_cast<const float4*>(v);
 #pragma unroll
   for (int k = 0; k < NT / 4; k++) {
-    float4 t = v4[k];
-    a[4 * k] = fmaf(s, t.x, a[4 * k]); a[4 * k + 1] = fmaf(s, t.y, a[4 * k + 1]);
-    a[4 * k + 2] = fmaf(s, t.z, a[4 * k + 2]); a[4 * k + 3] = fmaf(s, t.w, a[4 * k + 3]);
+    if ((cmask >> k) & 1) {
+      float4 t = v4[k];
+      a[4 * k] = fmaf(s, t.x, a[4 * k]); a[4 * k + 1] = fmaf(s, t.y, a[4 * k + 1]);
+      a[4 * k + 2] = fmaf(s, t.z, a[4 * k + 2]); a[4 * k + 3] = fmaf(s, t.w, a[4 * k + 3]);
+    }
   }
+}
+// packed Jacobian rows: position of dof i among the set bits of the contact's dof mask
+__device__ __forceinline__ int mask_pos(unsigned lo, unsigned hi, int i) {
+  return i < 32 ? __popc(lo & ((1u << i) - 1)) : __popc(lo) + __popc(hi & ((1u << (i - 32)) - 1));
+}
+__device__ __forceinline__ bool mask_has(unsigned lo, unsigned hi, int i) { return ((i < 32 ? lo >> i : hi >> (i - 32)) & 1) != 0; }
+// dense[0..ldj) = the packed row expanded (zeros elsewhere); every lane takes part
+__device__ __forceinline__ void expand_row(float* dense, const float* Jr, unsigned lo, unsigned hi, int ldj, int lane) {
+  _Pragma("unroll 1") for (int i = lane; i < ldj; i += 32) dense[i] = mask_has(lo, hi, i) ? Jr[mask_pos(lo, hi, i)] : 0.f;
+  __syncwarp();
 }
 // Right-looking Cholesky of the register rows a[0..NT) (lane i = row i; entries k > i are don't-care,
 // rows >= n are identity rows, lanes >= NT idle) FUSED with the solve of L L^T x = b:
@@ -293,7 +305,7 @@ __device__ __noinline__ float4 eval_constraints(const Rows R, float alpha, int l
   return res;   // cost, derivative, curvature
 }
 
-// y[r] = J[r,:] . x for all rows (simple rows + dense contact rows)
+// y[r] = J[r,:] . x for all rows (simple rows + packed contact rows)
 __device__ __noinline__ void mul_J(const Rows R, float* y, const float* x, int lane) {
   _Pragma("unroll 1") for (int r = lane; r < R.nefc; r += 32) {
     float s;
@@ -302,9 +314,14 @@ __device__ __noinline__ void mul_J(const Rows R, float* y, const float* x, int l
       int d2 = R.sd2[r];
       if (d2 >= 0) s += R.sc2[r] * x[d2];
     } else {
-      const float* Jr = R.J + (r - R.ns) * R.ldj;
+      const float* con = R.con + INFO_ID(R.info[r]) * CON_STRIDE;
+      unsigned lo = __float_as_uint(con[C_MASKLO]), hi = __float_as_uint(con[C_MASKHI]);
+      int w = __popc(lo) + __popc(hi);
+      const float* Jr = R.J + __float_as_int(con[C_JOFS]) + (r - __float_as_int(con[C_EFC])) * w;
       s = 0;
-      for (int k = 0; k < R.nv; k++) s += Jr[k] * x[k];
+      int k = 0;
+      while (lo) { int d = __ffs(lo) - 1; lo &= lo - 1; s += Jr[k++] * x[d]; }
+      while (hi) { int d = __ffs(hi) - 1; hi &= hi - 1; s += Jr[k++] * x[32 + d]; }
     }
     y[r] = s;
   }
@@ -319,8 +336,14 @@ __device__ __noinline__ void mul_JT(const Rows R, float* y, const float* f, int 
       if (R.sd1[r] == i) s += R.sc1[r] * f[r];
       if (R.sd2[r] == i) s += R.sc2[r] * f[r];
     }
-    const float* Jc = R.J + i;
-    for (int r = R.ns; r < R.nefc; r++) s += Jc[(r - R.ns) * R.ldj] * f[r];
+    for (int c = 0; c < R.ncon; c++) {
+      const float* con = R.con + c * CON_STRIDE;
+      unsigned lo = __float_as_uint(con[C_MASKLO]), hi = __float_as_uint(con[C_MASKHI]);
+      if (!mask_has(lo, hi, i)) continue;
+      int w = __popc(lo) + __popc(hi), dim = __float_as_int(con[C_DIM]), r0 = __float_as_int(con[C_EFC]);
+      const float* Jc = R.J + __float_as_int(con[C_JOFS]) + mask_pos(lo, hi, i);
+      for (int j = 0; j < dim; j++) s += Jc[j * w] * f[r0 + j];
+    }
     y[i] = s;
   }
   __syncwarp();
@@ -369,11 +392,23 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
 #pragma unroll 1
   for (int r = ns; r < R.nefc; r++) {
     int inf = R.info[r], st = INFO_STATE(inf);
+    if (st != ST_QUADRATIC && st != ST_CONE) continue;
+    // packed rows of this contact: lane i's entry sits at position pos (if dof i is in the mask); the rank-1 operands are
+    // expanded into dense scratch rows, and only the 4-column chunks that hold a dof of the contact are touched
+    const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+    const unsigned lo = __float_as_uint(con[C_MASKLO]), hi = __float_as_uint(con[C_MASKHI]), cm = __float_as_uint(con[C_CMASK]);
+    const int w = __popc(lo) + __popc(hi), r0 = __float_as_int(con[C_EFC]);
+    const float* Jc = R.J + __float_as_int(con[C_JOFS]);
+    const bool mine = lane < nv && mask_has(lo, hi, lane);
+    const int pos = mask_pos(lo, hi, lane);
+    float* dense = tmpJ + 2 * ldj;
     if (st == ST_QUADRATIC) {
-      const float* Jr = R.J + (r - ns) * ldj;
-      rank1_row<NT>(h, (lane < nv) ? R.eD[r] * Jr[lane] : 0.f, Jr);
-    } else if (st == ST_CONE) {
-      const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+      float jl = mine ? Jc[(r - r0) * w + pos] : 0.f;
+      __syncwarp();
+      if (lane < ldj) dense[lane] = jl;
+      __syncwarp();
+      rank1_row<NT>(h, R.eD[r] * jl, dense, cm);
+    } else {
       int dim = __float_as_int(con[C_DIM]);
       float mu = con[C_MU], U[6], sc[6], T2 = 0;
       sc[0] = mu; U[0] = R.jar[r] * mu;
@@ -383,28 +418,35 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
       }
       float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
       float iT = 1.0f / T;
-      const float* Jc = R.J + (r - ns) * ldj;
       // Exact cone Hessian in the scaled coordinates U (s = Dm/2 (N - mu T)^2):
       //   Hc = Dm g g^T + c (I_t - u u^T),  g = (1, -mu u),  u = U_t / T,  c = -Dm mu (N - mu T) / T  (> 0)
       // so J^T Hc J is dim+1 rank-1 updates: Dm vg vg^T - c vu vu^T + sum_j c sc_j^2 J_j J_j^T with
       // vg = sum_j sc_j g_j J_j and vu = sum_{j>=1} sc_j u_j J_j.
       float c = -Dm * mu * (N - mu * T) * iT;
-      int jl = min(lane, ldj - 1);
-      float vg = mu * Jc[jl], vu = 0;
+      float vg = 0.f, vu = 0.f;
+      if (mine) {
+        vg = mu * Jc[pos];
 #pragma unroll
-      for (int j = 1; j < 6; j++) {
-        if (j < dim) {
-          float w = sc[j] * U[j] * iT, Jj = Jc[j * ldj + jl];
-          vu = fmaf(w, Jj, vu); vg = fmaf(-mu * w, Jj, vg);
+        for (int j = 1; j < 6; j++) {
+          if (j < dim) {
+            float ww = sc[j] * U[j] * iT, Jj = Jc[j * w + pos];
+            vu = fmaf(ww, Jj, vu); vg = fmaf(-mu * ww, Jj, vg);
+          }
         }
       }
       __syncwarp();
-      if (lane < ldj) { tmpJ[lane] = lane < nv ? vg : 0.f; tmpJ[ldj + lane] = lane < nv ? vu : 0.f; }
+      if (lane < ldj) { tmpJ[lane] = vg; tmpJ[ldj + lane] = vu; }
       __syncwarp();
-      rank1_row<NT>(h, (lane < nv) ? Dm * vg : 0.f, tmpJ);
-      rank1_row<NT>(h, (lane < nv) ? -c * vu : 0.f, tmpJ + ldj);
+      rank1_row<NT>(h, Dm * vg, tmpJ, cm);
+      rank1_row<NT>(h, -c * vu, tmpJ + ldj, cm);
 #pragma unroll 1
-      for (int j = 1; j < dim; j++) { float fj = con[C_FRICTION + j - 1]; rank1_row<NT>(h, (lane < nv) ? c * fj * fj * Jc[j * ldj + jl] : 0.f, Jc + j * ldj); }
+      for (int j = 1; j < dim; j++) {
+        float fj = con[C_FRICTION + j - 1], jl = mine ? Jc[j * w + pos] : 0.f;
+        __syncwarp();
+        if (lane < ldj) dense[lane] = jl;
+        __syncwarp();
+        rank1_row<NT>(h, c * fj * fj * jl, dense, cm);
+      }
       r += dim - 1;
     }
   }
@@ -417,17 +459,19 @@ __device__ __noinline__ bool hessian_solve(const Rows R, float* H, const float* 
 // NT2 columns in a1).  Same right-looking scheme: the column shuffles of the first tile serve both rows, the
 // trailing columns 32.. only live in the second tile.  Rows in [n, NT2) are identity rows, rows >= NT2 are zero.
 template <int NT2>
-__device__ __forceinline__ void rank1_row2(float (&a0)[32], float (&a1)[NT2], float s0, float s1, const float* v, int ldv) {
+__device__ __forceinline__ void rank1_row2(float (&a0)[32], float (&a1)[NT2], float s0, float s1, const float* v, unsigned cmask) {
   const float4* v4 = reinterpret_cast<const float4*>(v);
 #pragma unroll
   for (int k = 0; k < NT2 / 4; k++) {
-    float4 t = (4 * k < ldv) ? v4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < 8) {
-      a0[4 * k] = fmaf(s0, t.x, a0[4 * k]); a0[4 * k + 1] = fmaf(s0, t.y, a0[4 * k + 1]);
-      a0[4 * k + 2] = fmaf(s0, t.z, a0[4 * k + 2]); a0[4 * k + 3] = fmaf(s0, t.w, a0[4 * k + 3]);
+    if ((cmask >> k) & 1) {
+      float4 t = v4[k];
+      if (k < 8) {
+        a0[4 * k] = fmaf(s0, t.x, a0[4 * k]); a0[4 * k + 1] = fmaf(s0, t.y, a0[4 * k + 1]);
+        a0[4 * k + 2] = fmaf(s0, t.z, a0[4 * k + 2]); a0[4 * k + 3] = fmaf(s0, t.w, a0[4 * k + 3]);
+      }
+      a1[4 * k] = fmaf(s1, t.x, a1[4 * k]); a1[4 * k + 1] = fmaf(s1, t.y, a1[4 * k + 1]);
+      a1[4 * k + 2] = fmaf(s1, t.z, a1[4 * k + 2]); a1[4 * k + 3] = fmaf(s1, t.w, a1[4 * k + 3]);
     }
-    a1[4 * k] = fmaf(s1, t.x, a1[4 * k]); a1[4 * k + 1] = fmaf(s1, t.y, a1[4 * k + 1]);
-    a1[4 * k + 2] = fmaf(s1, t.z, a1[4 * k + 2]); a1[4 * k + 3] = fmaf(s1, t.w, a1[4 * k + 3]);
   }
 }
 template <int NT2>
@@ -543,12 +587,23 @@ __device__ __noinline__ bool hessian_solve2(const Rows R, float* H, const float*
 #pragma unroll 1
     for (int r = ns; r < R.nefc; r++) {
       int inf = R.info[r], st = INFO_STATE(inf);
+      if (st != ST_QUADRATIC && st != ST_CONE) continue;
+      const float* con = R.con + INFO_ID(inf) * CON_STRIDE;   // packed rows, dense scratch operands, chunk mask: see hessian_solve
+      const unsigned lo = __float_as_uint(con[C_MASKLO]), hi = __float_as_uint(con[C_MASKHI]), cm = __float_as_uint(con[C_CMASK]);
+      const int w = __popc(lo) + __popc(hi), r0 = __float_as_int(con[C_EFC]);
+      const float* Jc = R.J + __float_as_int(con[C_JOFS]);
+      const bool mine0 = ((lo >> lane) & 1) != 0, mine1 = has1 && ((hi >> lane) & 1) != 0;
+      const int pos0 = __popc(lo & ((1u << lane) - 1)), pos1 = __popc(lo) + __popc(hi & ((1u << lane) - 1));
+      float* dense = tmpJ + 2 * ldj;
       if (st == ST_QUADRATIC) {
-        const float* Jr = R.J + (r - ns) * ldj;
-        float D = R.eD[r];
-        rank1_row2<NT2>(h0, h1, D * Jr[lane], has1 ? D * Jr[32 + lane] : 0.f, Jr, ldj);
-      } else if (st == ST_CONE) {
-        const float* con = R.con + INFO_ID(inf) * CON_STRIDE;
+        const float* Jr = Jc + (r - r0) * w;
+        float j0 = mine0 ? Jr[pos0] : 0.f, j1 = mine1 ? Jr[pos1] : 0.f, D = R.eD[r];
+        __syncwarp();
+        dense[lane] = j0;
+        if (32 + lane < ldj) dense[32 + lane] = j1;
+        __syncwarp();
+        rank1_row2<NT2>(h0, h1, D * j0, D * j1, dense, cm);
+      } else {
         int dim = __float_as_int(con[C_DIM]);
         float mu = con[C_MU], U[6], sc[6], T2 = 0;
         sc[0] = mu; U[0] = R.jar[r] * mu;
@@ -558,29 +613,31 @@ __device__ __noinline__ bool hessian_solve2(const Rows R, float* H, const float*
         }
         float N = U[0], T = sqrtf(T2), Dm = R.eD[r] / fmaxf(mu * mu * (1 + mu * mu), MINVAL);
         float iT = 1.0f / T;
-        const float* Jc = R.J + (r - ns) * ldj;
         float c = -Dm * mu * (N - mu * T) * iT;   // see hessian_solve for the rank-1 form of the cone Hessian
-        int j1 = has1 ? 32 + lane : lane;
-        float vg0 = mu * Jc[lane], vu0 = 0, vg1 = mu * Jc[j1], vu1 = 0;
+        float vg0 = mine0 ? mu * Jc[pos0] : 0.f, vu0 = 0, vg1 = mine1 ? mu * Jc[pos1] : 0.f, vu1 = 0;
 #pragma unroll
         for (int j = 1; j < 6; j++) {
           if (j < dim) {
-            float w = sc[j] * U[j] * iT, Ja = Jc[j * ldj + lane], Jb = Jc[j * ldj + j1];
-            vu0 = fmaf(w, Ja, vu0); vg0 = fmaf(-mu * w, Ja, vg0);
-            vu1 = fmaf(w, Jb, vu1); vg1 = fmaf(-mu * w, Jb, vg1);
+            float ww = sc[j] * U[j] * iT, Ja = mine0 ? Jc[j * w + pos0] : 0.f, Jb = mine1 ? Jc[j * w + pos1] : 0.f;
+            vu0 = fmaf(ww, Ja, vu0); vg0 = fmaf(-mu * ww, Ja, vg0);
+            vu1 = fmaf(ww, Jb, vu1); vg1 = fmaf(-mu * ww, Jb, vg1);
           }
         }
-        if (!has1) { vg1 = 0.f; vu1 = 0.f; }
         __syncwarp();
         tmpJ[lane] = vg0; tmpJ[ldj + lane] = vu0;
         if (32 + lane < ldj) { tmpJ[32 + lane] = vg1; tmpJ[ldj + 32 + lane] = vu1; }
         __syncwarp();
-        rank1_row2<NT2>(h0, h1, Dm * vg0, Dm * vg1, tmpJ, ldj);
-        rank1_row2<NT2>(h0, h1, -c * vu0, -c * vu1, tmpJ + ldj, ldj);
+        rank1_row2<NT2>(h0, h1, Dm * vg0, Dm * vg1, tmpJ, cm);
+        rank1_row2<NT2>(h0, h1, -c * vu0, -c * vu1, tmpJ + ldj, cm);
 #pragma unroll 1
         for (int j = 1; j < dim; j++) {
           float fj = con[C_FRICTION + j - 1], cf = c * fj * fj;
-          rank1_row2<NT2>(h0, h1, cf * Jc[j * ldj + lane], has1 ? cf * Jc[j * ldj + 32 + lane] : 0.f, Jc + j * ldj, ldj);
+          float j0 = mine0 ? Jc[j * w + pos0] : 0.f, j1 = mine1 ? Jc[j * w + pos1] : 0.f;
+          __syncwarp();
+          dense[lane] = j0;
+          if (32 + lane < ldj) dense[32 + lane] = j1;
+          __syncwarp();
+          rank1_row2<NT2>(h0, h1, cf * j0, cf * j1, dense, cm);
         }
         r += dim - 1;
       }
@@ -1698,63 +1755,67 @@ __device__ __forceinline__ void make_constraints(const DevModel& m, float* S, co
   }
   int ns = row0;
   ns_out = ns;
-  // contacts: dense Jacobian rows, lane = dof
+  // contacts: packed Jacobian rows (only the dofs on exactly one of the two bodies' chains), lane = dof
   float* J = S + o.J;
   const float *cdof = S + o.cdof, *xpos = G + o.xpos;   // G: the env's global block (part B)
-  int crow = 0, nv = m.nv, ldj = o.ldj;
+  int crow = 0, jn = 0, nv = m.nv;
   for (int c = 0; c < ncon; c++) {
     float* con = S + o.con + c * CON_STRIDE;
     int dim = __float_as_int(con[C_DIM]);
-    if (crow + dim > m.maxcrow) { flags |= 2; ncon = c; break; }
     int b1 = __float_as_int(con[C_BODY1]), b2 = __float_as_int(con[C_BODY2]), pair = __float_as_int(con[C_PAIR]);
+    const unsigned m2lo = PKI(body_dofmask)[2 * b2], m2hi = PKI(body_dofmask)[2 * b2 + 1];
+    const unsigned lo = (unsigned)PKI(body_dofmask)[2 * b1] ^ m2lo, hi = (unsigned)PKI(body_dofmask)[2 * b1 + 1] ^ m2hi;
+    const int w = __popc(lo) + __popc(hi);
+    if (crow + dim > m.maxcrow || jn + dim * w > m.maxjnz) { flags |= 2; ncon = c; break; }
     float pos[3] = {con[C_POS], con[C_POS + 1], con[C_POS + 2]};
     _Pragma("unroll 1") for (int i = lane; i < nv; i += 32) {
-      bool in1 = (PKI(body_dofmask)[2 * b1 + (i >> 5)] >> (i & 31)) & 1, in2 = (PKI(body_dofmask)[2 * b2 + (i >> 5)] >> (i & 31)) & 1;
-      float jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
-      if (in1 != in2) {
-        float sg = in2 ? 1.f : -1.f;
-        const float *cd = cdof + 6 * i, *ref = xpos + 3 * PKI(root_list)[PKI(body_rootidx)[PKI(dof_bodyid)[i]]];
-        float off[3] = {pos[0] - ref[0], pos[1] - ref[1], pos[2] - ref[2]}, t[3];
-        cross3(t, cd, off);
-        jr[0] = sg * cd[0]; jr[1] = sg * cd[1]; jr[2] = sg * cd[2];
-        jp[0] = sg * (cd[3] + t[0]); jp[1] = sg * (cd[4] + t[1]); jp[2] = sg * (cd[5] + t[2]);
-      }
+      if (!mask_has(lo, hi, i)) continue;
+      float sg = mask_has(m2lo, m2hi, i) ? 1.f : -1.f;
+      const float *cd = cdof + 6 * i, *ref = xpos + 3 * PKI(root_list)[PKI(body_rootidx)[PKI(dof_bodyid)[i]]];
+      float off[3] = {pos[0] - ref[0], pos[1] - ref[1], pos[2] - ref[2]}, t[3];
+      cross3(t, cd, off);
+      float jr[3] = {sg * cd[0], sg * cd[1], sg * cd[2]};
+      float jp[3] = {sg * (cd[3] + t[0]), sg * (cd[4] + t[1]), sg * (cd[5] + t[2])};
+      float* Jc = J + jn + mask_pos(lo, hi, i);
       for (int r = 0; r < dim; r++) {
         const float* ax = con + C_FRAME + 3 * (r < 3 ? r : r - 3);
-        J[(crow + r) * ldj + i] = (r < 3) ? dot3(ax, jp) : dot3(ax, jr);
+        Jc[r * w] = (r < 3) ? dot3(ax, jp) : dot3(ax, jr);
       }
     }
-    // the row padding [nv, ldj) is read by the float4 operand loads of the Hessian build: it must be zero
-    // (0 x stale NaN bit patterns would poison the identity rows of the register tile)
-    if (lane < ldj - nv) for (int r = 0; r < dim; r++) J[(crow + r) * ldj + nv + lane] = 0.f;
     __syncwarp();
     if (lane < dim) {
       int r = lane, row = ns + crow + r;
-      const float* Jr = J + (crow + r) * ldj;
+      const float* Jr = J + jn + r * w;
       float vel = 0;
-      for (int i = 0; i < nv; i++) vel += Jr[i] * qvel[i];
+      { unsigned a = lo, b = hi; int k = 0;
+        while (a) { int d = __ffs(a) - 1; a &= a - 1; vel += Jr[k++] * qvel[d]; }
+        while (b) { int d = __ffs(b) - 1; b &= b - 1; vel += Jr[k++] * qvel[32 + d]; } }
       float diag = (r < 3) ? (PKF(body_invweight0)[2 * b1] + PKF(body_invweight0)[2 * b2])
                            : (PKF(body_invweight0)[2 * b1 + 1] + PKF(body_invweight0)[2 * b2 + 1]);
       float R, aref;
       const float *solref = m.pair_solref + 2 * pair, *solimp = m.pair_solimp + 5 * pair;
       float inclmargin = m.pair_margin[pair] - m.pair_gap[pair];
       row_params(m.timestep, solref, solimp, r == 0 ? con[C_DIST] : 0.f, r == 0 ? inclmargin : 0.f, diag, vel, &R, &aref);
-      eR[row] = R; earef[row] = aref;
+      eD[row] = R; earef[row] = aref;   // contact rows keep only D = 1 / R (inverted below); R itself is needed for friction-loss rows only
       einfo[row] = ((dim == 1) ? CNSTR_CONTACT_FRICTIONLESS : CNSTR_CONTACT_ELLIPTIC) | (c << 8);
     }
     __syncwarp();
     if (lane == 0) {
       int row = ns + crow;
       con[C_EFC] = __int_as_float(row);
+      unsigned cm = 0;
+      for (int k = 0; k < 16; k++) if (((k < 8 ? lo >> (4 * k) : hi >> (4 * k - 32)) & 0xFu) != 0) cm |= 1u << k;
+      con[C_MASKLO] = __uint_as_float(lo); con[C_MASKHI] = __uint_as_float(hi);
+      con[C_JOFS] = __int_as_float(jn); con[C_CMASK] = __uint_as_float(cm);
       if (dim > 1) {
-        float R0 = eR[row], R1 = R0 / fmaxf(MINVAL, m.impratio), f0 = con[C_FRICTION];
-        eR[row + 1] = R1;
+        float R0 = eD[row], R1 = R0 / fmaxf(MINVAL, m.impratio), f0 = con[C_FRICTION];
+        eD[row + 1] = R1;
         con[C_MU] = f0 * sqrtf(R1 / R0);
-        for (int j = 2; j < dim; j++) { float fj = con[C_FRICTION + j - 1]; eR[row + j] = R1 * f0 * f0 / (fj * fj); }
+        for (int j = 2; j < dim; j++) { float fj = con[C_FRICTION + j - 1]; eD[row + j] = R1 * f0 * f0 / (fj * fj); }
       }
-      for (int j = 0; j < dim; j++) eD[row + j] = 1.f / eR[row + j];
+      for (int j = 0; j < dim; j++) eD[row + j] = 1.f / eD[row + j];
     }
-    crow += dim;
+    crow += dim; jn += dim * w;
   }
   __syncwarp();
   nefc_out = ns + crow;

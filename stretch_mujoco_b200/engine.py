@@ -21,7 +21,7 @@ CMD_WIDTH = 44
 
 EXPORTS = [
     "ss_model_load_blob", "ss_model_free", "ss_model_dims", "ss_name2id", "ss_id2name", "ss_model_get", "ss_model_field_info",
-    "ss_model_set", "ss_batch_create", "ss_batch_free", "ss_batch_reset", "ss_batch_step", "ss_batch_forward",
+    "ss_model_set", "ss_batch_create", "ss_batch_free", "ss_batch_reset", "ss_batch_step", "ss_batch_forward", "ss_batch_profile_step",
     "ss_batch_launch_count", "ss_batch_set_debug", "ss_batch_pull_status", "ss_batch_apply_commands",
     "ss_batch_step_controlled", "ss_batch_lidar",
     "ss_model_num_rangefinders", "ss_batch_rays", "ss_batch_render", "ss_batch_render_post", "ss_depth_colormap",
@@ -74,6 +74,7 @@ def lib():
         L.ss_batch_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ss_batch_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ss_batch_forward.argtypes = [C.c_void_p, C.c_void_p]
+        L.ss_batch_profile_step.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
         L.ss_batch_launch_count.restype = C.c_long
         L.ss_batch_launch_count.argtypes = [C.c_void_p]
         L.ss_batch_set_debug.argtypes = [C.c_void_p, C.POINTER(DebugBuffers)]
@@ -225,6 +226,12 @@ class Batch:
 
     def forward(self):
         _check(lib().ss_batch_forward(self._h, _stream()))
+
+    def profile_step(self):
+        """One mj_step with its kernels serialised and timed by CUDA events: (smooth, narrow, solve) in ms."""
+        ms = (C.c_float * 3)()
+        _check(lib().ss_batch_profile_step(self._h, ms, _stream()))
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def step_controlled(self, nsteps: int = 1):
         """nsteps x (apply_commands, one physics step): the reference's per-step command cadence."""

@@ -144,13 +144,13 @@ class StatusStretchSensors:
 class StretchMujocoSimulator:
     def __init__(self, scene_xml_path: str | None = None, model=None, camera_hz: float = 30,
                  cameras_to_use: list | None = None, start_translation=None, start_rotation_quat=None, *,
-                 nenv: int = 1, device: int = 0, model_blob: bytes | None = None, maxcon: int = 32,
+                 nenv: int = 1, device: int = 0, model_blob: bytes | None = None, maxcon: int = 32, maxefc: int = 0,
                  with_render: bool | None = None):
         self.scene_xml_path, self.model_blob = scene_xml_path, model_blob
         self.camera_hz = camera_hz
         self.cameras_to_use = list(cameras_to_use or [])
         self.start_translation, self.start_rotation_quat = start_translation, start_rotation_quat
-        self.nenv, self.device, self.maxcon = nenv, device, maxcon
+        self.nenv, self.device, self.maxcon, self.maxefc = nenv, device, maxcon, maxefc
         self.with_render = bool(self.cameras_to_use) if with_render is None else with_render
         self._running = False
         self.batch = None
@@ -179,7 +179,7 @@ class StretchMujocoSimulator:
             if self.start_rotation_quat is not None:
                 q0[3:7] = self.start_rotation_quat
             self.dmodel.set("qpos0", q0)
-        self.batch = engine.Batch(self.dmodel, self.nenv, maxcon=self.maxcon)
+        self.batch = engine.Batch(self.dmodel, self.nenv, maxcon=self.maxcon, maxefc=self.maxefc)
         self._act = {n: self.dmodel.name2id(engine.OBJ_ACTUATOR, n) for n in
                      ["lift", "arm", "head_pan", "head_tilt", "wrist_yaw", "wrist_pitch", "wrist_roll", "gripper",
                       "left_wheel_vel", "right_wheel_vel"]}

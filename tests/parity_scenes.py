@@ -52,5 +52,5 @@ def run(title, name, maxcon, maxefc, nenv=16, nsteps=1000):
 
 
 print("\n## Other scenes (16 envs x 1000 steps, `home` command + per-env random lift / arm / head targets)")
-run("default scene.xml (dock, table, two free objects; nv = 44)", "stretch_default_scene.ssm", 64, 43 + 176)
+run("default scene.xml (dock, table, two free objects; nv = 44)", "stretch_default_scene.ssm", 72, 288)
 run("kitchen proxy (box fixtures + one free box; nv = 32)", "stretch_kitchen_proxy_render.ssm.z", 32, 0)

@@ -189,7 +189,7 @@ def test_default_scene_rollout_1000_steps():
     """The reference's default scene.xml (dock on the floor with 30 plane-mesh contacts, table, box and cylinder on
     it; nv = 44, 44-49 contacts): exact contact lists for the first 100 steps, median qpos error <= 1e-4 after
     1000 steps; envs whose arm sweeps into the dock / table fork on MPR contacts and are bounded at 0.2."""
-    B, e, same, first100 = _settled_rollout("stretch_default_scene.ssm", 64, 43 + 176)
+    B, e, same, first100 = _settled_rollout("stretch_default_scene.ssm", 72, 288)
     print("default scene: rel qpos median %.1e max %.1e, contact history equal %d/16 (first 100 steps: %d/16)" % (np.median(e), e.max(), same.sum(), first100.sum()))
     assert first100.sum() >= 15
     assert np.median(e) < 1e-4 and e.max() < 0.2
