@@ -452,6 +452,13 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   if (wpb < 1 || wpb1 < 1) { delete B; return ss_fail("env working set (%zu B + %zu B model pack) exceeds shared memory (%d B)", B->smem_per_env, pack_bytes, max_smem); }
   wpb = std::min(wpb, 8);     // ss_solve_kernel: __launch_bounds__(256, 1), up to 255 registers per thread
   wpb1 = std::min(wpb1, 16);  // ss_smooth_kernel: __launch_bounds__(512, 1)
+  // small batches (strong scaling: 512 envs per GPU) spread over all SMs instead of filling a few CTAs: a step's latency
+  // is one warp's dependent chain whatever the CTA size, and fewer warps per CTA wait for fewer neighbours
+  {
+    const int per_sm = (nenv + sms - 1) / sms;
+    wpb = std::max(std::min(wpb, 2), std::min(wpb, per_sm));
+    wpb1 = std::max(std::min(wpb1, 2), std::min(wpb1, per_sm));
+  }
   if (const char* e = getenv("SS_WPB")) wpb = std::max(1, std::min(wpb, atoi(e)));   // tuning knobs (A/B experiments; results never depend on them)
   if (const char* e = getenv("SS_WPB1")) wpb1 = std::max(1, std::min(wpb1, atoi(e)));
   B->sync_level = 9;   // 1: stage barriers in the smooth kernel, 8: lockstep Newton loop in the solve kernel (physics.cu)

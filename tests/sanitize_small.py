@@ -9,7 +9,7 @@ rawE = open(bench.GOLDEN, "rb").read()
 A, _ = blob.unpack(rawE)
 for r, nenv, nsteps in ((rawE, 24, int(os.environ.get("NSTEPS", 6))), (raw, 5, 3)):
     dm = engine.DeviceModel(r, 0)
-    B = engine.Batch(dm, nenv, maxcon=32)
+    B = engine.Batch(dm, nenv, maxcon=32 if r is rawE else 72, maxefc=0 if r is rawE else 288)
     if r is rawE:
         lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device="cuda"); hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device="cuda")
         B.ctrl.copy_(bench.ctrl_torch(0, 0, nenv, 0, lo, hi, "cuda"))
@@ -21,4 +21,6 @@ for r, nenv, nsteps in ((rawE, 24, int(os.environ.get("NSTEPS", 6))), (raw, 5, 3
         d = B.lidar(); cam = dm.name2id(engine.OBJ_CAMERA, "d405_rgb")
         rgb = torch.zeros(nenv, 27, 48, 3, dtype=torch.uint8, device="cuda"); dep = torch.zeros(nenv, 27, 48, device="cuda")
         B.render(cam, 48, 27, 58.0, rgb, dep); torch.cuda.synchronize()
+        rgb2 = torch.zeros(nenv, 120, 160, 3, dtype=torch.uint8, device="cuda"); dep2 = torch.zeros(nenv, 120, 160, device="cuda")
+        B.render(dm.name2id(engine.OBJ_CAMERA, "d435i_camera_rgb"), 160, 120, 42.0, rgb2, dep2, 10.0); torch.cuda.synchronize()   # raster path incl. large boxes
     print("ok", nenv, float(B.qpos.abs().sum()))

@@ -381,3 +381,25 @@ def test_raster_camera_path_matches_the_ray_cast_path():
         assert close.mean() > 0.9995, close.mean()
         assert (np.abs(c1.astype(int) - c2.astype(int)).max(axis=-1) <= 1).mean() > 0.999
         assert (d2 > 0).mean() > 0.05
+
+
+def test_profile_step_is_a_step(gpu, arrays_E, settled_home_E):
+    """ss_batch_profile_step (the per-kernel timing aid behind bench.py's roofline line) advances the state exactly like
+    ss_batch_step(1) and returns three positive kernel durations."""
+    from stretch_mujoco_b200 import engine
+    q0, v0, w0, home = settled_home_E
+    outs = []
+    for mode in (0, 1):
+        B = engine.Batch(gpu, 300)
+        for dst, src in ((B.qpos, q0), (B.qvel, v0), (B.qacc_warmstart, w0), (B.ctrl, home)):
+            dst.copy_(torch.tensor(np.tile(src, (300, 1)), dtype=torch.float32))
+        B.ctrl[:, 2] = torch.linspace(0.3, 1.0, 300, device="cuda")
+        for _ in range(5):
+            if mode:
+                ms = B.profile_step()
+                assert all(0.0 < x < 100.0 for x in ms), ms
+            else:
+                B.step(1)
+        torch.cuda.synchronize()
+        outs.append((B.qpos.clone(), B.qvel.clone(), B.time.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
