@@ -188,6 +188,9 @@ def compile_scene(sc: Scene, with_render: bool = True, verbose: bool = False) ->
             dataid = -1
             if gtype == "mesh":
                 ma = get_mesh(g["mesh"])
+                # MuJoCo >= 3.3 moved the switch from the geom (shellinertia="true") to the mesh asset (inertia="shell"):
+                # models/stretch_mj_3.3.0.xml:129-222
+                shell = shell or sc.meshes.get(g["mesh"], {}).get("inertia", "") == "shell"
                 if g["mesh"] not in mesh_ids:
                     mesh_ids[g["mesh"]] = len(mesh_list); mesh_list.append(ma)
                 dataid = mesh_ids[g["mesh"]]

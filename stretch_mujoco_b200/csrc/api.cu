@@ -433,9 +433,9 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   m.maxcrow = maxefc > 0 ? std::max(maxefc - nsimple, 6) : 160;
   m.maxrow = m.maxsimple + m.maxcrow;
   // packed contact Jacobian: a row holds only the dofs between the two bodies' chains (wheel on floor: 7, wrist on base: ~10, free
-  // object on table: 6), 12 floats per row of capacity cover the measured workloads (an overflow drops the contact and
+  // object on table: 6), 14 floats per row of capacity cover the measured workloads (an overflow drops the contact and
   // sets env_flags bit 1, like the row capacity), but any single contact (6 rows of nv) must fit
-  m.maxjnz = std::max(m.maxcrow * 12, 6 * ((m.nv + 3) & ~3));
+  m.maxjnz = std::max(m.maxcrow * 14, 6 * ((m.nv + 3) & ~3));
   if (const char* e = getenv("SS_MAXJNZ")) m.maxjnz = std::max(m.maxjnz / 4, atoi(e));
   B->dm1 = m;
   B->smem_per_env = (size_t)build_layout(m, 3) * sizeof(float);

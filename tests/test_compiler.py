@@ -1,5 +1,7 @@
 """Scene loader / model compiler checks.  CPU only.
 Tests that read the reference's MJCF files skip when /root/reference is not mounted."""
+import os
+
 import numpy as np
 import pytest
 
@@ -210,3 +212,22 @@ def test_mjmodel_npz_import_round_trip(tmp_path, blob_empty_floor):
         om.step(q, v, arrays["key_ctrl"][0][None].copy(), w, nsteps=50)
         qs.append(q)
     assert np.array_equal(qs[0], qs[1])
+
+
+@needs_ref
+def test_stretch_mj_3_3_0_variant_compiles_to_the_same_robot():
+    """models/stretch_mj_3.3.0.xml moves the shell-inertia switch from the geoms to the mesh assets
+    (inertia="shell", :129-222), gives the cameras their own fovy (:378,456,463) and drops the lidar replicate: same
+    bodies, dofs and mass properties as stretch.xml, five cameras with fovy 58 / 69 where the file sets them."""
+    from stretch_mujoco_b200 import compiler, mjcf, scenes
+    d = scenes.models_dir()
+    new = compiler.compile_scene(mjcf.Scene.from_xml_path(os.path.join(d, "stretch_mj_3.3.0.xml")), with_render=False)
+    old = compiler.compile_scene(mjcf.Scene.from_xml_path(os.path.join(d, "stretch.xml")), with_render=False)
+    a, b = new.arrays, old.arrays
+    assert list(a["sizes"][:6]) == list(b["sizes"][:6])                       # nq nv nu nbody njnt ngeom
+    for k in ("body_mass", "body_inertia", "body_ipos", "body_iquat", "jnt_range", "actuator_biasprm"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["sizes"][6] == 1 and b["sizes"][6] == 361                        # sites: the lidar replicate is gone
+    cams = new.names[4]
+    fovy = dict(zip(cams, a["cam_fovy"]))
+    assert fovy["d405_rgb"] == 58.0 and fovy["d435i_camera_rgb"] == 58.0 and fovy["nav_camera_rgb"] == 69.0
