@@ -471,7 +471,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
             B->pack_bytes, m.pk.nwords3 * 4, B->smem_per_env1, wpb1, B->smem_per_env, wpb, m.L.pb, m.L.pbA, max_smem);
   B->grid = std::min((nenv + wpb - 1) / wpb, sms);
   B->grid1 = std::min((nenv + wpb1 - 1) / wpb1, sms);
-  B->grid2 = 2 * sms;
+  B->grid2 = 2 * sms;   // ss_narrow_kernel: __launch_bounds__(256, 2) (three CTAs of 80 registers per SM measured slower: 45.9 vs 43.4 ms per bench step)
   // pipeline scratch: persistent blocks, broadphase slots, narrowphase records, work-item queue
   B->maxslot = std::max(32, 3 * m.maxcon);   // broadphase candidates per env (global scratch only)
   if (const char* e = getenv("SS_MAXSLOT")) B->maxslot = std::max(8, atoi(e));

@@ -145,7 +145,7 @@ def test_default_scene_physics_forward_parity(scene):
     B.forward(); torch.cuda.synchronize()
     o = om.forward(qpos, qvel, ctrl, None, maxcon=32, want=("M", "contact_geom", "nefc", "qfrc_constraint", "qacc_smooth"))
     M = B.dbg["M"].cpu().numpy()
-    assert np.abs(M - o["M"]).max() <= 1e-5 * np.abs(o["M"]).max()
+    assert np.abs(M - o["M"]).max() <= 1e-6 * np.abs(o["M"]).max()
     assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])
     assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
     qs = B.dbg["qacc_smooth"].cpu().numpy()
@@ -192,10 +192,11 @@ def test_kitchen_proxy_physics_lidar_and_cameras(kitchen):
     assert np.array_equal(B.contact_geom.cpu().numpy(), o["contact_geom"])
     assert np.array_equal(B.dbg["nefc"].cpu().numpy(), o["nefc"])
     M = B.dbg["M"].cpu().numpy()
-    assert np.abs(M - o["M"]).max() <= 1e-5 * np.abs(o["M"]).max()
+    assert np.abs(M - o["M"]).max() <= 1e-6 * np.abs(o["M"]).max()
     qa = B.qacc.cpu().numpy()
     rel = np.abs(qa - o["qacc"]).max(1) / (np.abs(o["qacc"]).max(1) + 1e-3)
-    assert np.median(rel) < 1e-3 and rel.max() < 2e-2, rel
+    print("kitchen forward: qacc rel median %.1e max %.1e" % (np.median(rel), rel.max()))
+    assert np.median(rel) < 1e-3 and rel.max() < 2e-3, rel      # measured 5.6e-4 / 6.9e-4: the resting box sits on four box-box contacts of ~1e-7 m depth noise
     # lidar: 1000 rays per env against the oracle (walls, counter, stove, tap, robot's own meshes)
     dist = B.lidar().cpu().numpy()
     xpos, xquat = f(B.xpos), f(B.xquat)
