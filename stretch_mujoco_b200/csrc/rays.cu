@@ -1104,12 +1104,75 @@ __global__ void __launch_bounds__(256) raster_large_kernel(RayModel r, int W, in
     const float invf = 1.0f / campose[16 * it.le + 12];
     unsigned long long* zb = zbuf + (size_t)it.le * W * H;
     const RTri& b = it.t;
-    const int bw = b.u1 - b.u0 + 1, n = bw * (b.v1 - b.v0 + 1);
-    for (int idx = lane; idx < n; idx += 32) raster_pixel(b, b.u0 + idx % bw, b.v0 + idx / bw, W, H, invf, znear, zfar, zb);
+    // lanes stride over the band's pixels in row-major order; (u, v) advance without a division per pixel
+    const int bw = b.u1 - b.u0 + 1;
+    int u = b.u0 + lane % bw, v = b.v0 + lane / bw;
+    const int du = 32 % bw, dv = 32 / bw;
+    while (v <= b.v1) {
+      raster_pixel(b, u, v, W, H, invf, znear, zfar, zb);
+      u += du; v += dv;
+      if (u > b.u1) { u -= bw; v++; }
+    }
   }
 }
 
-// per pixel: analytic primitives by ray casting, merge with the depth/id buffer, shade, store, reset the buffer
+// Pixel epilogue of the raster path: the arithmetic of shade_and_store with the per-frame constants hoisted (vector loads of
+// the material and the geom rotation, light directions normalised once per CTA: lvec[.][3] < 0 marks a unit direction).
+__device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, const float* hn, const float* dw, const float* cam_eye,
+                                           const float (*lvec)[4], const float (*lcol)[9], int nslot, const float* xf, float zfar, size_t pix,
+                                           uint8_t* __restrict__ rgb, float* __restrict__ depth, float depth_limit, int bgr) {
+  if (x < 0 || x > zfar) { x = zfar; k = -1; }
+  if (depth) depth[pix] = (depth_limit > 0 && x > depth_limit) ? 0.f : x;   // utils.limit_depth_distance
+  if (!rgb) return;
+  float col[3];
+  const float idw = rsqrtf(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);
+  if (k < 0) {
+    float tt = 0.5f * (1.0f + dw[2] * idw);
+#pragma unroll
+    for (int a = 0; a < 3; a++) col[a] = r.nsky >= 2 ? tt * r.sky[a] + (1 - tt) * r.sky[3 + a] : 0.f;
+  } else {
+    const float4* sh4 = reinterpret_cast<const float4*>(r.rg_shade + 8 * k);
+    const float4 s0 = __ldg(sh4), s1 = __ldg(sh4 + 1);          // rgb, (unused alpha slot = sh[3]); specular, shininess, emission, -
+    const float4* x4 = reinterpret_cast<const float4*>(xf + 12 * k);
+    const float4 t0 = x4[0], t1 = x4[1], t2 = x4[2];            // pos.xyz R00 | R01 R02 R10 R11 | R12 R20 R21 R22
+    float n[3] = {t0.w * hn[0] + t1.x * hn[1] + t1.y * hn[2], t1.z * hn[0] + t1.w * hn[1] + t2.x * hn[2], t2.y * hn[0] + t2.z * hn[1] + t2.w * hn[2]};
+    float inv = rsqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    n[0] *= inv; n[1] *= inv; n[2] *= inv;
+    const float pos[3] = {cam_eye[0] + x * dw[0], cam_eye[1] + x * dw[1], cam_eye[2] + x * dw[2]};
+    const float vw[3] = {-dw[0] * idw, -dw[1] * idw, -dw[2] * idw};
+    if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    const float base[3] = {s0.x, s0.y, s0.z}, spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
+#pragma unroll
+    for (int a = 0; a < 3; a++) col[a] = base[a] * emis;
+    for (int l = 0; l < nslot; l++) {
+      const float* lv = lvec[l];
+      const float* lc = lcol[l];
+      float L[3] = {lv[0], lv[1], lv[2]};
+      if (lv[3] > 0.f) {   // positional light
+        L[0] -= pos[0]; L[1] -= pos[1]; L[2] -= pos[2];
+        float il = rsqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+        L[0] *= il; L[1] *= il; L[2] *= il;
+      }
+      float nl = fmaxf(n[0] * L[0] + n[1] * L[1] + n[2] * L[2], 0.f), hs = 0.f;
+      if (nl > 0) {
+        float hv[3] = {L[0] + vw[0], L[1] + vw[1], L[2] + vw[2]};
+        float ih = rsqrtf(hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2]);
+        hs = __powf(fmaxf((n[0] * hv[0] + n[1] * hv[1] + n[2] * hv[2]) * ih, 0.f), shininess);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++) col[a] += base[a] * (lc[a] + lc[3 + a] * nl) + spec * lc[6 + a] * hs;
+    }
+  }
+  uint8_t* px = rgb + 3 * pix;
+#pragma unroll
+  for (int a = 0; a < 3; a++) px[bgr ? 2 - a : a] = (uint8_t)(fminf(fmaxf(col[a], 0.f), 1.f) * 255.0f + 0.5f);
+}
+
+#define MAXPLANE 4
+struct SPlane { float n[3], c0, ax[3], ox, ay[3], oy, s0, s1; int k; };   // world normal, n . (eye - p); in-plane axes / offsets for sized planes
+
+// per pixel: analytic primitives by ray casting (planes through a precomputed world-space form), merge with the depth/id
+// buffer, shade, store, reset the buffer
 __global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env_begin, int out_begin, int cam, int W, int H,
                                                              const float* __restrict__ xpos, const float* __restrict__ xquat,
                                                              const float* __restrict__ xf_all, const float* __restrict__ campose,
@@ -1118,24 +1181,58 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env
   __shared__ float cam_eye[3], cam_R[9], focal;
   __shared__ float lvec[MAXLIGHT][4];
   __shared__ float lcol[MAXLIGHT][9];
-  __shared__ int sprim[MAXPRIM], nprim;
+  __shared__ int sprim[MAXPRIM], nprim, nplane, nslot;
+  __shared__ SPlane planes[MAXPLANE];
   const int le = blockIdx.z, e = env_begin + le, tid = threadIdx.y * 32 + threadIdx.x;
+  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
   if (tid < 13) {
     float x = campose[16 * le + tid];
     if (tid < 3) cam_eye[tid] = x; else if (tid < 12) cam_R[tid - 3] = x; else focal = x;
   }
-  if (tid == 13) nprim = prim[(size_t)le * (MAXPRIM + 1)];
   if (rgb && tid >= 14 && tid < 15 + r.nlight && tid < 14 + MAXLIGHT) light_colours(r, tid - 14, lcol[tid - 14]);
-  if (tid >= 64 && tid < 64 + MAXPRIM) sprim[tid - 64] = prim[(size_t)le * (MAXPRIM + 1) + 1 + tid - 64];
-  if (rgb && tid >= 32 && tid < 32 + r.nlight && tid < 32 + MAXLIGHT - 1) light_vector(r, tid - 32, xpos, xquat, e, lvec[tid - 31]);
+  if (rgb && tid >= 32 && tid < 32 + r.nlight && tid < 32 + MAXLIGHT - 1) {
+    float* L = lvec[tid - 31];
+    light_vector(r, tid - 32, xpos, xquat, e, L);
+    if (L[3] == 0.f) {   // directional: normalise once
+      float il = rsqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+      L[0] *= il; L[1] *= il; L[2] *= il;
+    }
+  }
   __syncthreads();
-  if (tid == 0) { lvec[0][0] = cam_R[2]; lvec[0][1] = cam_R[5]; lvec[0][2] = cam_R[8]; lvec[0][3] = 0.f; }   // headlight
+  if (tid == 0) {
+    // slot 0 = headlight along the camera's +z; inactive headlight: the scene lights move down one slot
+    const int nl = min(r.nlight, MAXLIGHT - 1);
+    if (r.headlight_active) { lvec[0][0] = cam_R[2]; lvec[0][1] = cam_R[5]; lvec[0][2] = cam_R[8]; lvec[0][3] = 0.f; nslot = nl + 1; }
+    else {
+      for (int l = 0; l < nl; l++) { for (int a = 0; a < 4; a++) lvec[l][a] = lvec[l + 1][a]; for (int a = 0; a < 9; a++) lcol[l][a] = lcol[l + 1][a]; }
+      nslot = nl;
+    }
+    // planes leave the generic list: t = -n . (eye - p) / (n . d) per pixel
+    const int n0 = prim[(size_t)le * (MAXPRIM + 1)];
+    int np = 0, npl = 0;
+    for (int i = 0; i < n0; i++) {
+      const int k = prim[(size_t)le * (MAXPRIM + 1) + 1 + i];
+      const float4* rec = r.rg_rec + 4 * k;
+      if (REC_TYPE(rec) == GEOM_PLANE && npl < MAXPLANE) {
+        const float *T = xf + 12 * k, *R = T + 3;
+        SPlane& P = planes[npl++];
+        const float dif[3] = {cam_eye[0] - T[0], cam_eye[1] - T[1], cam_eye[2] - T[2]};
+        P.n[0] = R[2]; P.n[1] = R[5]; P.n[2] = R[8];
+        P.ax[0] = R[0]; P.ax[1] = R[3]; P.ax[2] = R[6];
+        P.ay[0] = R[1]; P.ay[1] = R[4]; P.ay[2] = R[7];
+        P.c0 = P.n[0] * dif[0] + P.n[1] * dif[1] + P.n[2] * dif[2];
+        P.ox = P.ax[0] * dif[0] + P.ax[1] * dif[1] + P.ax[2] * dif[2];
+        P.oy = P.ay[0] * dif[0] + P.ay[1] * dif[1] + P.ay[2] * dif[2];
+        P.s0 = rec[1].y; P.s1 = rec[1].z; P.k = k;
+      } else sprim[np++] = k;
+    }
+    nprim = np; nplane = npl;
+  }
   __syncthreads();
   const int u = blockIdx.x * 32 + threadIdx.x;
   if (u >= W) return;
   const float invf = 1.0f / focal, znear = r.znear * r.extent, zfar = r.zfar * r.extent;
-  const float* xf = xf_all + (size_t)e * r.nraygeom * 12;
-  const int np = nprim;
+  const int np = nprim, npl = nplane, ns = nslot, rot = (post >> 1) & 3, bgr = post & 1, lo = out_begin + le;
 #pragma unroll 1
   for (int row = 0; row < 4; row++) {   // a 32 x 32 pixel tile per CTA: the prologue above is paid once per 1024 pixels
     const int v = blockIdx.y * 32 + row * 8 + threadIdx.y;
@@ -1143,10 +1240,23 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env
     float dl[3] = {(u + 0.5f - 0.5f * W) * invf, -(v + 0.5f - 0.5f * H) * invf, -1.0f};   // same rays as raster_pixel
     float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
                    cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
-    Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
     unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
     const unsigned long long key = *z;
-    {
+    Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+    for (int i = 0; i < npl; i++) {
+      const SPlane& P = planes[i];
+      const float d2 = P.n[0] * dw[0] + P.n[1] * dw[1] + P.n[2] * dw[2];
+      if (d2 > -1e-15f) continue;
+      const float x = -P.c0 / d2;
+      if (x < znear || (h.t >= 0 && x >= h.t)) continue;
+      if (P.s0 > 0 || P.s1 > 0) {
+        const float px = P.ox + x * (P.ax[0] * dw[0] + P.ax[1] * dw[1] + P.ax[2] * dw[2]);
+        const float py = P.oy + x * (P.ay[0] * dw[0] + P.ay[1] * dw[1] + P.ay[2] * dw[2]);
+        if ((P.s0 > 0 && fabsf(px) > P.s0) || (P.s1 > 0 && fabsf(py) > P.s1)) continue;
+      }
+      h.t = x; h.k = P.k; h.n[0] = 0.f; h.n[1] = 0.f; h.n[2] = 1.f;
+    }
+    if (np) {
       const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
       for (int i = 0; i < np; i++) trace_one<false>(r, xf, r.rg_rec, sprim[i], cam_eye, dw, vv, znear, 0, -1, h);
     }
@@ -1161,7 +1271,10 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env
         h.n[0] = e1.y * e2.z - e1.z * e2.y; h.n[1] = e1.z * e2.x - e1.x * e2.z; h.n[2] = e1.x * e2.y - e1.y * e2.x;
       }
     }
-    shade_and_store(r, h, dw, cam_eye, lvec, lcol, xf, zfar, out_begin + le, u, v, W, H, rgb, depth, depth_limit, post);
+    const size_t pix = rot == 0 ? ((size_t)lo * H + v) * W + u
+                     : rot == 1 ? ((size_t)lo * W + (W - 1 - u)) * H + v
+                                : ((size_t)lo * W + u) * H + (H - 1 - v);
+    shade_fast(r, h.t, h.k, h.n, dw, cam_eye, lvec, lcol, ns, xf, zfar, pix, rgb, depth, depth_limit, bgr);
   }
 }
 
