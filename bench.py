@@ -47,7 +47,7 @@ NAV = ("nav_camera_rgb", 800, 600, 102.0, 0.0, True, False)
 CONFIGS = {
     "cfg2": dict(blob="stretch_empty_floor.ssm", mj_steps=50, cams=[], lidar=False, maxcon=32,
                  workload="cfg2: {n} parallel Stretch envs per GPU, empty-floor scene, physics only (no sensors)"),
-    "default": dict(blob="stretch_default_scene.ssm", mj_steps=50, cams=[], lidar=False, maxcon=72, maxefc=288,
+    "default": dict(blob="stretch_default_scene.ssm", mj_steps=50, cams=[], lidar=False, maxcon=72, maxefc=320,
                     workload="default scene.xml (dock, table, two free objects; nv = 44): {n} envs per GPU, physics only"),
     "cfg3": dict(blob="stretch_empty_floor_render.ssm.z", mj_steps=5, cams=[HEAD640], lidar=False, maxcon=32,
                  workload="cfg3: {n} envs per GPU, empty floor, physics + 640x480 head RGB+depth render after every mj_step"),

@@ -489,6 +489,8 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
     return ss_fail("ss_batch_create: schedule buffers: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (const char* e = getenv("SS_RENDER")) B->render_mode = strcmp(e, "raycast") == 0 ? 0 : 1;   // A/B knob: the ray-cast camera path
+  if (const char* e = getenv("SS_RASTER_NSUB")) B->raster_nsub = std::max(1, atoi(e));
+  B->raster_stats = getenv("SS_RASTER_STATS") != nullptr;
   B->nosort = getenv("SS_NOSORT") != nullptr;
   // schedule key: bucket = min(255, cost_scale * cost), cost = cost_w x Newton iterations + narrowphase queries
   // (47.3 ms per 50 steps for 16 / x1 against 47.9 ms for 8 / x4)
@@ -572,7 +574,7 @@ static int launch_physics(ss_batch* B, int nsteps, int forward_only, ss_stream s
   // that the other set's tails leave idle.
   const int cost_scale = B->cost_scale;
   cudaStream_t user = (cudaStream_t)stream;
-  int nsets = (forward_only || nsteps < 2 || marks) ? 1 : B->nsets;
+  int nsets = (forward_only || marks) ? 1 : B->nsets;   // single steps fork too: the sets' chains fill each other's kernel tails
   if (nsets > 1) {
     CUDA_OK(cudaEventRecord(B->ev_fork, user));
     for (int k = 0; k < nsets; k++) CUDA_OK(cudaStreamWaitEvent(B->side[k], B->ev_fork, 0));

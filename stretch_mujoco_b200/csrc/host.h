@@ -59,6 +59,8 @@ struct ss_batch {
   int* rs_qcount = nullptr;
   int rs_qcap = 0;
   int rs_nsub = 0;
+  int raster_nsub = 0;                       // SS_RASTER_NSUB: envs per raster sub-chunk (0 = automatic)
+  bool raster_stats = false;                 // SS_RASTER_STATS: print work counters per sub-chunk (diagnostic)
 };
 
 int ss_fail(const char* fmt, ...);

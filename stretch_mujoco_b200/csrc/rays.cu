@@ -1346,7 +1346,7 @@ extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fo
     // sub-chunks of up to 256 envs (measured at 640x480, 4096 envs: 20 envs 61.4 ms, 40 envs 49.0 ms, 128 envs 39.5 ms, 256 envs 37.6 ms:
     // amortising the launch tails beats keeping the depth/id buffer L2-resident); at most 1 GiB of buffer
     int nsub = (int)std::max<size_t>(1, std::min<size_t>(256, ((size_t)1 << 30) / (npix * 8)));
-    if (const char* e = getenv("SS_RASTER_NSUB")) nsub = std::max(1, atoi(e));   // tuning knob (results do not depend on it)
+    if (B->raster_nsub > 0) nsub = B->raster_nsub;   // SS_RASTER_NSUB, read once at batch creation (tuning knob; results do not depend on it)
     nsub = std::min(nsub, env_count);
     if (B->zbuf_cap < npix * nsub) {
       if (B->zbuf) { CUDA_OK(cudaStreamSynchronize(st)); cudaFree(B->zbuf); B->zbuf = nullptr; }
@@ -1369,7 +1369,7 @@ extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fo
       const int n = std::min(nsub, env_count - off), e0 = env_begin + off;
       raster_setup_kernel<<<n, 256, 0, st>>>(r, e0, cam, W, H, fovy, B->bufs.xpos, B->bufs.xquat, B->ray_xf, B->rs_cam, B->rs_prim, B->rs_cvis);
       unsigned long long* stats = nullptr;
-      if (getenv("SS_RASTER_STATS")) { cudaMalloc((void**)&stats, 16 * 8); cudaMemsetAsync(stats, 0, 16 * 8, st); }
+      if (B->raster_stats) { cudaMalloc((void**)&stats, 16 * 8); cudaMemsetAsync(stats, 0, 16 * 8, st); }   // SS_RASTER_STATS=1: work counters (diagnostic, synchronises)
       CUDA_OK(cudaMemsetAsync(B->rs_qcount, 0, sizeof(int), st));
       raster_tri_kernel<<<dim3(r.nchunk, n), 128, 0, st>>>(r, e0, W, H, B->ray_xf, B->rs_cam, B->rs_cvis, B->zbuf, stats,
                                                            (RItem*)B->rs_queue, B->rs_qcount, B->rs_qcap);
