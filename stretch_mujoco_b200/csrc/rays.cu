@@ -1142,8 +1142,8 @@ __device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, co
     const float vw[3] = {-dw[0] * idw, -dw[1] * idw, -dw[2] * idw};
     if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
     const float base[3] = {s0.x, s0.y, s0.z}, spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
-#pragma unroll
-    for (int a = 0; a < 3; a++) col[a] = base[a] * emis;
+    // col = base * (emission + sum_l (ambient_l + diffuse_l nl_l)) + specular * sum_l specular_l hs_l
+    float da[3] = {emis, emis, emis}, sa[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < nslot; l++) {
       const float* lv = lvec[l];
       const float* lc = lcol[l];
@@ -1160,8 +1160,10 @@ __device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, co
         hs = __powf(fmaxf((n[0] * hv[0] + n[1] * hv[1] + n[2] * hv[2]) * ih, 0.f), shininess);
       }
 #pragma unroll
-      for (int a = 0; a < 3; a++) col[a] += base[a] * (lc[a] + lc[3 + a] * nl) + spec * lc[6 + a] * hs;
+      for (int a = 0; a < 3; a++) { da[a] += lc[a] + lc[3 + a] * nl; sa[a] = fmaf(lc[6 + a], hs, sa[a]); }
     }
+#pragma unroll
+    for (int a = 0; a < 3; a++) col[a] = base[a] * da[a] + spec * sa[a];
   }
   uint8_t* px = rgb + 3 * pix;
 #pragma unroll

@@ -6,11 +6,11 @@ import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import bench
 from stretch_mujoco_b200 import engine, blob
-raw = open(bench.GOLDEN, "rb").read()
+raw = blob.read_bytes(os.path.join(bench.GOLDEN_DIR, os.environ.get("BLOB", "stretch_empty_floor.ssm")))
 A, _ = blob.unpack(raw)
 dm = engine.DeviceModel(raw, 0)
 nenv = int(os.environ.get("NENV", 4096)); nsteps = int(os.environ.get("NSTEPS", 10))
-B = engine.Batch(dm, nenv)
+B = engine.Batch(dm, nenv, maxcon=int(os.environ.get("MAXCON", 32)), maxefc=int(os.environ.get("MAXEFC", 0)))
 dev = B.qpos.device
 lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev); hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
 for p in range(3):
