@@ -110,6 +110,13 @@ om_model* om_model_load(const void* buf, size_t nbytes) {
     I(light_directional, "light_directional"); D(light_ambient, "light_ambient"); D(light_diffuse, "light_diffuse");
     D(light_specular, "light_specular"); m->nlight = (int)ss_blob_count(&b, "light_bodyid");
     m->headlight_active = ss_blob_i32(&b, "vis_headlight_active")[0];
+    if (ss_blob_find(&b, "geom_tex")) {
+      D(geom_tex, "geom_tex"); I(tex_adr, "tex_adr"); I(tex_w, "tex_w"); I(tex_h, "tex_h");
+      m->ntex = (int)ss_blob_count(&b, "tex_adr");
+      size_t c2 = ss_blob_count(&b, "tex_rgb");
+      const unsigned char* tp = ss_blob_u8(&b, "tex_rgb");
+      m->tex_rgb = (unsigned char*)malloc(c2 ? c2 : 1); if (c2 && tp) memcpy(m->tex_rgb, tp, c2);
+    }
   }
 #undef D
 #undef I

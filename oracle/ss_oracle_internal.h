@@ -48,6 +48,9 @@ struct om_model {
   int *rmesh_vertadr, *rmesh_faceadr, *rmesh_facenum, *rmesh_bvhadr, *rmesh_face, *bvh_child, *raygeom_id;
   float *rmesh_vert, *bvh_aabb;
   double *geom_shade, *vis_headlight, *vis_map, *skybox_rgb;
+  double* geom_tex;                 /* [ngeom,4] texture index (-1 none), texrepeat x/y, texuniform (NULL: blob without textures) */
+  int *tex_adr, *tex_w, *tex_h, ntex;
+  unsigned char* tex_rgb;
   int *light_bodyid, *light_directional;
   double *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;
 };

@@ -319,9 +319,37 @@ typedef struct {
   unsigned char* rgb; float* depth;
 } render_ctx;
 
+/* bilinear sample of 2-D texture t at (s, t) with GL_REPEAT wrapping; texel centres at (i + 0.5) / w, image row 0 on top
+   (t = 1) [upstream: mjr uploads the PNG rows bottom-up] */
+static void tex_sample(const om_model* m, int t, double s, double tt, double* rgb) {
+  int w = m->tex_w[t], h = m->tex_h[t];
+  const unsigned char* img = m->tex_rgb + m->tex_adr[t];
+  double x = (s - floor(s)) * w - 0.5, y = (1.0 - (tt - floor(tt))) * h - 0.5;
+  int x0 = (int)floor(x), y0 = (int)floor(y);
+  double fx = x - x0, fy = y - y0;
+  int xa = ((x0 % w) + w) % w, xb = (xa + 1) % w, ya = ((y0 % h) + h) % h, yb = (ya + 1) % h;
+  for (int k = 0; k < 3; k++) {
+    double c00 = img[3 * (ya * w + xa) + k], c10 = img[3 * (ya * w + xb) + k], c01 = img[3 * (yb * w + xa) + k], c11 = img[3 * (yb * w + xb) + k];
+    rgb[k] = ((c00 * (1 - fx) + c10 * fx) * (1 - fy) + (c01 * (1 - fx) + c11 * fx) * fy) / 255.0;
+  }
+}
+
 static void shade_pixel(const om_model* m, int g, const double* pos, const double* nrm_in, const double* eye,
-                        const double* fwd, const double* xpos, const double* xquat, unsigned char* out) {
-  const double* sh = m->geom_shade + 8 * g;
+                        const double* fwd, const double* xpos, const double* xquat, const double* gpos, const double* gmat,
+                        unsigned char* out) {
+  double sh[8];
+  for (int k = 0; k < 8; k++) sh[k] = m->geom_shade[8 * g + k];
+  if (m->geom_tex && m->geom_tex[4 * g] >= 0) {
+    /* planar x-y projection of the geom frame; texrepeat per unit length (texuniform) or per geom extent */
+    const double* tx = m->geom_tex + 4 * g;
+    double d[3] = {pos[0] - gpos[0], pos[1] - gpos[1], pos[2] - gpos[2]};
+    double lx = gmat[0] * d[0] + gmat[3] * d[1] + gmat[6] * d[2], ly = gmat[1] * d[0] + gmat[4] * d[1] + gmat[7] * d[2];
+    double sx = m->geom_size[3 * g], sy = m->geom_size[3 * g + 1], s, t, c[3];
+    if (tx[3] != 0 || sx <= 0 || sy <= 0) { s = lx * tx[1]; t = ly * tx[2]; }
+    else { s = (lx / (2 * sx) + 0.5) * tx[1]; t = (ly / (2 * sy) + 0.5) * tx[2]; }
+    tex_sample(m, (int)tx[0], s, t, c);
+    for (int k = 0; k < 3; k++) sh[k] *= c[k];
+  }
   double n[3] = {nrm_in[0], nrm_in[1], nrm_in[2]}, v[3], col[3];
   v3normalize(n);
   v3sub(v, eye, pos); v3normalize(v);
@@ -388,7 +416,7 @@ static void render_env(const om_model* m, om_data* d, int e, void* vctx) {
         } else {
           double pos[3];
           v3addscl(pos, eye, dw, x);
-          shade_pixel(m, g, pos, nrm, eye, fwd, xpos, xquat, px);
+          shade_pixel(m, g, pos, nrm, eye, fwd, xpos, xquat, d->geom_xpos + 3 * g, d->geom_xmat + 9 * g, px);
         }
       }
     }

@@ -203,6 +203,33 @@ int ss_rays_model_init(ss_model* M) {
     rec[4 * k + 3] = make_float4(hi[0], hi[1], hi[2], 0);
   }
   r.rg_rec = upload(M, rec);
+  {
+    std::vector<float4> rgtex(rg.size(), make_float4(-1.f, 1.f, 1.f, 0.f));
+    std::vector<int4> tinfo;
+    std::vector<unsigned char> texels;
+    if (ss_blob_find(&b, "geom_tex") && ss_blob_count(&b, "tex_adr") > 0) {
+      const double* gt = ss_blob_f64(&b, "geom_tex");
+      const int32_t *ta = ss_blob_i32(&b, "tex_adr"), *tw = ss_blob_i32(&b, "tex_w"), *th = ss_blob_i32(&b, "tex_h");
+      const unsigned char* tp = ss_blob_u8(&b, "tex_rgb");
+      size_t nt = ss_blob_count(&b, "tex_adr"), nb = ss_blob_count(&b, "tex_rgb");
+      if (gt && ta && tw && th && tp) {
+        bool ok = true;
+        for (size_t t = 0; t < nt; t++) {
+          if (ta[t] < 0 || tw[t] <= 0 || th[t] <= 0 || (size_t)ta[t] + (size_t)tw[t] * th[t] * 3 > nb) ok = false;
+          tinfo.push_back(make_int4(ta[t], tw[t], th[t], 0));
+        }
+        if (ok) {
+          texels.assign(tp, tp + nb);
+          for (size_t k = 0; k < rg.size(); k++) {
+            const double* g4 = gt + 4 * (size_t)rg[k];
+            if (g4[0] >= 0 && g4[0] < (double)nt) rgtex[k] = make_float4((float)g4[0], (float)g4[1], (float)g4[2], (float)g4[3]);
+          }
+        } else tinfo.clear();
+      }
+    }
+    r.ntex = (int)tinfo.size();
+    r.rg_tex = upload(M, rgtex); r.tex_info = upload(M, tinfo); r.tex_rgb = upload(M, texels);
+  }
   // raster work chunks of the camera-visible mesh geoms (groups 0..2)
   {
     std::vector<int4> chunks; std::vector<float4> cbox;
@@ -656,6 +683,32 @@ __global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restr
 #define TILE 16
 #define TILES_PER_CTA 4   // horizontally adjacent tiles share one staging of the env's geoms
 #define MAXLIGHT 8
+// 2-D texture of ray-geom k at the world point pos (planar x-y projection of the geom frame, GL_REPEAT, bilinear, texel
+// centres at (i + 0.5) / w, image row 0 on top); multiplies the material colour
+__device__ __forceinline__ void texture_modulate(const RayModel& r, int k, const float* T, const float* pos, float* base) {
+  const float4 tx = __ldg(r.rg_tex + k);
+  if (tx.x < 0.f) return;
+  const float* R = T + 3;
+  const float d[3] = {pos[0] - T[0], pos[1] - T[1], pos[2] - T[2]};
+  const float lx = R[0] * d[0] + R[3] * d[1] + R[6] * d[2], ly = R[1] * d[0] + R[4] * d[1] + R[7] * d[2];
+  const float4 sz = __ldg(r.rg_rec + 4 * k + 1);   // (rbound, size.xyz)
+  float s, t;
+  if (tx.w != 0.f || sz.y <= 0.f || sz.z <= 0.f) { s = lx * tx.y; t = ly * tx.z; }
+  else { s = (lx / (2.f * sz.y) + 0.5f) * tx.y; t = (ly / (2.f * sz.z) + 0.5f) * tx.z; }
+  const int4 ti = __ldg(r.tex_info + (int)tx.x);
+  const int w = ti.y, h = ti.z;
+  const unsigned char* img = r.tex_rgb + ti.x;
+  const float x = (s - floorf(s)) * w - 0.5f, y = (1.0f - (t - floorf(t))) * h - 0.5f;
+  const int x0 = (int)floorf(x), y0 = (int)floorf(y);
+  const float fx = x - x0, fy = y - y0;
+  const int xa = ((x0 % w) + w) % w, xb = (xa + 1) % w, ya = ((y0 % h) + h) % h, yb = (ya + 1) % h;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float c00 = img[3 * (ya * w + xa) + a], c10 = img[3 * (ya * w + xb) + a], c01 = img[3 * (yb * w + xa) + a], c11 = img[3 * (yb * w + xb) + a];
+    base[a] *= ((c00 * (1 - fx) + c10 * fx) * (1 - fy) + (c01 * (1 - fx) + c11 * fx) * fy) * (1.0f / 255.0f);
+  }
+}
+
 // Pixel epilogue shared by the ray-cast and the raster camera paths: far clip, depth limit, Blinn-Phong restatement
 // of the fixed-function lighting, client-side post-processing of the reference fused in
 // (status_stretch_camera.py:47-82).  xf = the env's geom transforms (12 floats per ray-geom, shared or global memory).
@@ -688,7 +741,9 @@ __device__ __forceinline__ void shade_and_store(const RayModel& r, Hit h, const 
       inv = rsqrtf(vw[0] * vw[0] + vw[1] * vw[1] + vw[2] * vw[2]);
       vw[0] *= inv; vw[1] *= inv; vw[2] *= inv;
       if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
-      for (int a = 0; a < 3; a++) col[a] = sh[a] * sh[6];
+      float base[3] = {sh[0], sh[1], sh[2]};
+      if (r.ntex) texture_modulate(r, h.k, xf + 12 * h.k, pos, base);
+      for (int a = 0; a < 3; a++) col[a] = base[a] * sh[6];
       float shininess = fmaxf(sh[5] * 128.0f, 1.0f);
       int nl_ = min(r.nlight, MAXLIGHT - 1);
       for (int l = -1; l < nl_; l++) {
@@ -710,7 +765,7 @@ __device__ __forceinline__ void shade_and_store(const RayModel& r, Hit h, const 
           float ih = rsqrtf(hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2]);
           hs = __powf(fmaxf((n[0] * hv[0] + n[1] * hv[1] + n[2] * hv[2]) * ih, 0.f), shininess);
         }
-        for (int a = 0; a < 3; a++) col[a] += sh[a] * (amb[a] + dif[a] * nl) + sh[4] * spc[a] * hs;
+        for (int a = 0; a < 3; a++) col[a] += base[a] * (amb[a] + dif[a] * nl) + sh[4] * spc[a] * hs;
       }
     }
     uint8_t* px = rgb + 3 * pix;
@@ -1142,7 +1197,9 @@ __device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, co
     const float pos[3] = {cam_eye[0] + x * dw[0], cam_eye[1] + x * dw[1], cam_eye[2] + x * dw[2]};
     const float vw[3] = {-dw[0] * idw, -dw[1] * idw, -dw[2] * idw};
     if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
-    const float base[3] = {s0.x, s0.y, s0.z}, spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
+    float base[3] = {s0.x, s0.y, s0.z};
+    const float spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
+    if (r.ntex) texture_modulate(r, k, xf + 12 * k, pos, base);
     // col = base * (emission + sum_l (ambient_l + diffuse_l nl_l)) + specular * sum_l specular_l hs_l
     float da[3] = {emis, emis, emis}, sa[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < nslot; l++) {

@@ -25,6 +25,12 @@ struct RayModel {
   int nchunk;
   const int4* rchunk;
   const float4* rchunk_box;   // 2 per chunk: lo, hi
+  // 2-D textures of box / plane geoms (planar x-y projection of the geom frame): per ray-geom (texture index or -1, texrepeat x, y,
+  // texuniform), per texture (first byte, width, height), RGB8 texels (row 0 = top of the image)
+  const float4* rg_tex;
+  const int4* tex_info;
+  const unsigned char* tex_rgb;
+  int ntex;
   const int *light_bodyid, *light_directional;
   const float *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;
 };

@@ -10,6 +10,8 @@ is dropped here so that it is not traversed twice.
 Arrays added to the model (consumed by csrc/rays.cu and by the oracle):
   raygeom_id[n]            geom ids that rays test
   geom_shade[ngeom, 8]     rgb, alpha, specular, shininess, emission, reflectance
+  geom_tex[ngeom, 4]       2-D texture of the geom's material: texture index (-1 = none), texrepeat x / y, texuniform
+  tex_adr/tex_w/tex_h[ntex], tex_rgb u8 [sum h*w*3]   texture images (row 0 = top row of the file)
   rmesh_vertadr/faceadr/facenum[nmesh], rmesh_vert[*,3] f32, rmesh_face[*,3] i32 (mesh frame)
 Acceleration structures (BVHs) are built at load time by each consumer.
 """
@@ -36,6 +38,35 @@ def build_ray_geometry(m, verbose: bool = False) -> None:
             spec, shin, emis, refl = float(mt["specular"]), float(mt["shininess"]), float(mt["emission"]), float(mt["reflectance"])
         shade[gi] = [rgba[0], rgba[1], rgba[2], rgba[3], spec, shin, emis, refl]
     A["geom_shade"] = shade
+    # 2-D textures (`<texture type="2d" file=...>` behind a material, models/scene.xml:15-16): sampled on boxes and planes through
+    # the planar x-y projection of the geom frame [upstream: glTexGen OBJECT_LINEAR]; meshes would need their UV sets and keep
+    # the material colour
+    gtex = np.zeros((ngeom, 4)); gtex[:, 0] = -1
+    tex_ids, tex_imgs = {}, []
+    for gi, g in enumerate(flat_geoms):
+        mat = g.get("material")
+        if not mat or A["geom_type"][gi] not in (0, 6):
+            continue
+        mt = sc.materials[mat]
+        tname = mt.get("texture")
+        tx = sc.textures.get(tname) if tname else None
+        if not tx or tx.get("type", "cube") != "2d" or "path" not in tx:
+            continue
+        if tname not in tex_ids:
+            try:
+                from PIL import Image
+                img = np.asarray(Image.open(tx["path"]).convert("RGB"), dtype=np.uint8)
+            except Exception:
+                continue
+            tex_ids[tname] = len(tex_imgs); tex_imgs.append(img)
+        rep = _floats(mt.get("texrepeat", "1 1"), 2)
+        gtex[gi] = [tex_ids[tname], rep[0], rep[1], 1.0 if mt.get("texuniform", "false") == "true" else 0.0]
+    A["geom_tex"] = gtex
+    adr = np.cumsum([0] + [im.size for im in tex_imgs])[:-1] if tex_imgs else np.zeros(0)
+    A["tex_adr"] = np.asarray(adr, dtype=np.int32)
+    A["tex_w"] = np.asarray([im.shape[1] for im in tex_imgs], dtype=np.int32)
+    A["tex_h"] = np.asarray([im.shape[0] for im in tex_imgs], dtype=np.int32)
+    A["tex_rgb"] = np.concatenate([im.reshape(-1) for im in tex_imgs]) if tex_imgs else np.zeros(0, np.uint8)
     # candidate list with duplicate suppression
     keep = []
     seen = {}

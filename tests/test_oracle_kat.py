@@ -212,3 +212,41 @@ def test_startup_base_drift_anchor(blob_default_scene):
     assert 0.0044 / 3 < y < 0.0044 * 3                    # and a few millimetres to the left
     assert abs(theta) < 0.0650 * 1.5                      # yaw of the same order (its sign is not reproduced)
     assert np.abs(v[0, :6]).max() < 1e-6                  # and the base is at rest again (reference: ~1e-8)
+
+
+def _table_view(A, names, om):
+    """Head camera panned to the robot's right and tilted down: the wood table of scene.xml fills the lower half."""
+    jn = names[compiler.OBJ_JOINT]
+    q = A["qpos0"][None].copy()
+    q[0, A["jnt_qposadr"][jn.index("joint_head_pan")]] = -1.57
+    q[0, A["jnt_qposadr"][jn.index("joint_head_tilt")]] = -0.6
+    o = om.forward(q, np.zeros((1, om.nv)), A["key_ctrl"][0][None].copy(), None, want=("xpos", "xquat"))
+    return o, names[compiler.OBJ_CAMERA].index("d435i_camera_rgb")
+
+
+def test_wood_table_texture():
+    """`<texture type="2d" file="wood.png"/>` behind the table's material (models/scene.xml:15-16,25): the table top carries
+    the image (planar x-y projection of the box frame, bilinear, GL_REPEAT) modulated by the lighting.  Against the same model
+    with the texture switched off: only table pixels change, they show the grain, and their hue is the one the reference
+    printed for the bottom rows of its d405 frame, [160, 133, 100] (docs/getting_started.ipynb:414-416: R/B 1.6, G/B 1.33)."""
+    import os
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    raw = blob.read_bytes(os.path.join(os.path.dirname(__file__), "golden", "stretch_default_scene_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    assert int((A["geom_tex"][:, 0] >= 0).sum()) == 1 and A["tex_w"][0] == 512 and A["tex_h"][0] == 512
+    om = OracleModel(raw); om.set_options(enable_lidar=False)
+    o, cam = _table_view(A, names, om)
+    rgb, depth = om.render(o["xpos"], o["xquat"], cam, 96, 72, 42.0)
+    A2 = dict(A); A2["geom_tex"] = A["geom_tex"].copy(); A2["geom_tex"][:, 0] = -1
+    om2 = OracleModel(blob.pack(A2, names)); om2.set_options(enable_lidar=False)
+    rgb2, depth2 = om2.render(o["xpos"], o["xquat"], cam, 96, 72, 42.0)
+    assert np.array_equal(depth, depth2)
+    changed = np.abs(rgb.astype(int) - rgb2.astype(int)).max(-1)[0] > 0
+    assert 0.3 < changed.mean() < 0.8                                    # the table top, nothing else
+    assert 0.5 < depth[0][changed].min() and depth[0][changed].max() < 2.0
+    tex = rgb[0][changed].astype(float)
+    mean = tex.mean(0)
+    assert 1.4 < mean[0] / mean[2] < 1.8 and 1.2 < mean[1] / mean[2] < 1.45, mean
+    assert tex.std(0).min() > 5.0                                        # wood grain, not a flat colour
+    assert tex.std(0).min() > 1.5 * rgb2[0][changed].std(0).max()        # ... against the smooth shading of the untextured table

@@ -403,3 +403,34 @@ def test_profile_step_is_a_step(gpu, arrays_E, settled_home_E):
         torch.cuda.synchronize()
         outs.append((B.qpos.clone(), B.qvel.clone(), B.time.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
+def test_wood_table_texture_on_the_device():
+    """2-D texture sampling in the camera epilogue (raster path and ray-cast path) against the oracle: head camera panned onto
+    the wood table of the default scene; the table pixels carry the image, colours within 2 levels on >= 99 % of the pixels."""
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob, compiler, engine
+    raw = blob.read_bytes(os.path.join(GOLDEN, "stretch_default_scene_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    om = OracleModel(raw); om.set_options(enable_lidar=False)
+    dm = engine.DeviceModel(raw, 0)
+    jn = names[compiler.OBJ_JOINT]
+    for mode in ("raster", "raycast"):
+        os.environ["SS_RENDER"] = mode
+        try:
+            B = engine.Batch(dm, 2, maxcon=72, maxefc=320)
+        finally:
+            os.environ.pop("SS_RENDER", None)
+        B.reset()
+        B.qpos[:, int(A["jnt_qposadr"][jn.index("joint_head_pan")])] = -1.57
+        B.qpos[:, int(A["jnt_qposadr"][jn.index("joint_head_tilt")])] = -0.6
+        B.forward(); torch.cuda.synchronize()
+        cam = dm.name2id(engine.OBJ_CAMERA, "d435i_camera_rgb")
+        W, H = 192, 144
+        rgb = torch.zeros(2, H, W, 3, dtype=torch.uint8, device="cuda"); depth = torch.zeros(2, H, W, device="cuda")
+        B.render(cam, W, H, 42.0, rgb, depth, 10.0); torch.cuda.synchronize()
+        rrgb, rdepth = om.render(f64(B.xpos), f64(B.xquat), cam, W, H, 42.0)
+        c = rgb.cpu().numpy()
+        assert (np.abs(c.astype(int) - rrgb.astype(int)).max(axis=-1) <= 2).mean() > 0.99, mode
+        table = (rdepth[0] > 0.5) & (rdepth[0] < 2.0) & (rrgb[0, :, :, 0].astype(int) > rrgb[0, :, :, 2].astype(int) + 30)   # wood: red well above blue
+        assert table.mean() > 0.25 and c[0][table].std(0).min() > 5.0, mode
