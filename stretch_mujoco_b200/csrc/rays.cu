@@ -1229,11 +1229,39 @@ __device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, co
 }
 
 #define MAXPLANE 4
+#ifndef RESOLVE_CTAS
+#define RESOLVE_CTAS 5   // CTAs of 256 threads per SM (48 registers): occupancy beats register-resident constants (640x480 frame of 4096 envs: 2 CTAs 37.0 ms, 3 30.4, 4 27.1, 5 25.7, 6 26.3)
+#endif
 struct SPlane { float n[3], c0, ax[3], ox, ay[3], oy, s0, s1; int k; };   // world normal, n . (eye - p); in-plane axes / offsets for sized planes
 
 // per pixel: analytic primitives by ray casting (planes through a precomputed world-space form), merge with the depth/id
 // buffer, shade, store, reset the buffer
-__global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env_begin, int out_begin, int cam, int W, int H,
+__device__ __forceinline__ void plane_hit(const SPlane& P, const float* dw, float znear, Hit& h) {
+  const float d2 = P.n[0] * dw[0] + P.n[1] * dw[1] + P.n[2] * dw[2];
+  if (d2 > -1e-15f) return;
+  const float x = -P.c0 / d2;
+  if (x < znear || (h.t >= 0 && x >= h.t)) return;
+  if (P.s0 > 0 || P.s1 > 0) {
+    const float px = P.ox + x * (P.ax[0] * dw[0] + P.ax[1] * dw[1] + P.ax[2] * dw[2]);
+    const float py = P.oy + x * (P.ay[0] * dw[0] + P.ay[1] * dw[1] + P.ay[2] * dw[2]);
+    if ((P.s0 > 0 && fabsf(px) > P.s0) || (P.s1 > 0 && fabsf(py) > P.s1)) return;
+  }
+  h.t = x; h.k = P.k; h.n[0] = 0.f; h.n[1] = 0.f; h.n[2] = 1.f;
+}
+// the depth/id buffer's winner replaces the primitive hit when it is nearer
+__device__ __forceinline__ void merge_mesh_hit(const RayModel& r, unsigned long long key, Hit& h) {
+  const float x = __uint_as_float((unsigned)(key >> 32));
+  if (h.t < 0 || x < h.t) {
+    const unsigned id = (unsigned)key;
+    const size_t ti = id & 0x3fffffu;
+    const float4 e1 = __ldg(r.tri + 3 * ti + 1), e2 = __ldg(r.tri + 3 * ti + 2);
+    h.t = x; h.k = (int)(id >> 22);
+    h.n[0] = e1.y * e2.z - e1.z * e2.y; h.n[1] = e1.z * e2.x - e1.x * e2.z; h.n[2] = e1.x * e2.y - e1.y * e2.x;
+  }
+}
+
+template <int NSLOT>   // light slots known at launch (1..3: registers, unrolled), 0 = generic
+__global__ void __launch_bounds__(256, RESOLVE_CTAS) raster_resolve_kernel(RayModel r, int env_begin, int out_begin, int cam, int W, int H,
                                                              const float* __restrict__ xpos, const float* __restrict__ xquat,
                                                              const float* __restrict__ xf_all, const float* __restrict__ campose,
                                                              const int* __restrict__ prim, unsigned long long* __restrict__ zbuf,
@@ -1292,49 +1320,126 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RayModel r, int env
   const int u = blockIdx.x * 32 + threadIdx.x;
   if (u >= W) return;
   const float invf = 1.0f / focal, znear = r.znear * r.extent, zfar = r.zfar * r.extent;
-  const int np = nprim, npl = nplane, ns = nslot, rot = (post >> 1) & 3, bgr = post & 1, lo = out_begin + le;
+  const int np = nprim, npl = nplane, rot = (post >> 1) & 3, bgr = post & 1, lo = out_begin + le;
+  if constexpr (NSLOT == 0) {
+    // generic path: any number of light slots, everything read from shared memory per pixel
+    const int ns = nslot;
 #pragma unroll 1
-  for (int row = 0; row < 4; row++) {   // a 32 x 32 pixel tile per CTA: the prologue above is paid once per 1024 pixels
-    const int v = blockIdx.y * 32 + row * 8 + threadIdx.y;
-    if (v >= H) break;
-    float dl[3] = {(u + 0.5f - 0.5f * W) * invf, -(v + 0.5f - 0.5f * H) * invf, -1.0f};   // same rays as raster_pixel
-    float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
-                   cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
-    unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
-    const unsigned long long key = *z;
-    Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
-    for (int i = 0; i < npl; i++) {
-      const SPlane& P = planes[i];
-      const float d2 = P.n[0] * dw[0] + P.n[1] * dw[1] + P.n[2] * dw[2];
-      if (d2 > -1e-15f) continue;
-      const float x = -P.c0 / d2;
-      if (x < znear || (h.t >= 0 && x >= h.t)) continue;
-      if (P.s0 > 0 || P.s1 > 0) {
-        const float px = P.ox + x * (P.ax[0] * dw[0] + P.ax[1] * dw[1] + P.ax[2] * dw[2]);
-        const float py = P.oy + x * (P.ay[0] * dw[0] + P.ay[1] * dw[1] + P.ay[2] * dw[2]);
-        if ((P.s0 > 0 && fabsf(px) > P.s0) || (P.s1 > 0 && fabsf(py) > P.s1)) continue;
+    for (int row = 0; row < 4; row++) {   // a 32 x 32 pixel tile per CTA: the prologue above is paid once per 1024 pixels
+      const int v = blockIdx.y * 32 + row * 8 + threadIdx.y;
+      if (v >= H) break;
+      float dl[3] = {(u + 0.5f - 0.5f * W) * invf, -(v + 0.5f - 0.5f * H) * invf, -1.0f};   // same rays as raster_pixel
+      float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
+                     cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
+      unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
+      const unsigned long long key = *z;
+      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      for (int i = 0; i < npl; i++) plane_hit(planes[i], dw, znear, h);
+      if (np) {
+        const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+        for (int i = 0; i < np; i++) trace_one<false>(r, xf, r.rg_rec, sprim[i], cam_eye, dw, vv, znear, 0, -1, h);
       }
-      h.t = x; h.k = P.k; h.n[0] = 0.f; h.n[1] = 0.f; h.n[2] = 1.f;
+      if (key != ZEMPTY) { *z = ZEMPTY; merge_mesh_hit(r, key, h); }
+      const size_t pix = rot == 0 ? ((size_t)lo * H + v) * W + u
+                       : rot == 1 ? ((size_t)lo * W + (W - 1 - u)) * H + v
+                                  : ((size_t)lo * W + u) * H + (H - 1 - v);
+      shade_fast(r, h.t, h.k, h.n, dw, cam_eye, lvec, lcol, ns, xf, zfar, pix, rgb, depth, depth_limit, bgr);
     }
-    if (np) {
-      const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
-      for (int i = 0; i < np; i++) trace_one<false>(r, xf, r.rg_rec, sprim[i], cam_eye, dw, vv, znear, 0, -1, h);
+  } else {
+    // NSLOT light slots known at launch: camera, first plane and lights live in registers for the four rows of the tile
+    float cR[9], eye[3], Lv[NSLOT][4], Lc[NSLOT][9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) cR[k] = cam_R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) eye[k] = cam_eye[k];
+#pragma unroll
+    for (int l = 0; l < NSLOT; l++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) Lv[l][k] = lvec[l][k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Lc[l][k] = lcol[l][k];
     }
-    if (key != ZEMPTY) {
-      *z = ZEMPTY;
-      float x = __uint_as_float((unsigned)(key >> 32));
-      if (h.t < 0 || x < h.t) {
-        unsigned id = (unsigned)key;
-        size_t ti = id & 0x3fffffu;
-        float4 e1 = __ldg(r.tri + 3 * ti + 1), e2 = __ldg(r.tri + 3 * ti + 2);
-        h.t = x; h.k = (int)(id >> 22);
-        h.n[0] = e1.y * e2.z - e1.z * e2.y; h.n[1] = e1.z * e2.x - e1.x * e2.z; h.n[2] = e1.x * e2.y - e1.y * e2.x;
+    const bool p0 = npl > 0 && !(planes[0].s0 > 0 || planes[0].s1 > 0);   // first plane unbounded (a floor): inline form
+    const float pn[3] = {planes[0].n[0], planes[0].n[1], planes[0].n[2]}, pc0 = planes[0].c0;
+    const int pk = planes[0].k;
+    const float dx = (u + 0.5f - 0.5f * W) * invf;
+#pragma unroll 1
+    for (int row = 0; row < 4; row++) {
+      const int v = blockIdx.y * 32 + row * 8 + threadIdx.y;
+      if (v >= H) break;
+      const float dy = -(v + 0.5f - 0.5f * H) * invf;
+      const float dw[3] = {cR[0] * dx + cR[1] * dy - cR[2], cR[3] * dx + cR[4] * dy - cR[5], cR[6] * dx + cR[7] * dy - cR[8]};
+      unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
+      const unsigned long long key = *z;
+      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      if (p0) {
+        const float d2 = pn[0] * dw[0] + pn[1] * dw[1] + pn[2] * dw[2];
+        if (d2 <= -1e-15f) {
+          const float x = -pc0 / d2;
+          if (x >= znear) { h.t = x; h.k = pk; h.n[2] = 1.f; }
+        }
       }
+      for (int i = p0 ? 1 : 0; i < npl; i++) plane_hit(planes[i], dw, znear, h);
+      if (np) {
+        const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
+        for (int i = 0; i < np; i++) trace_one<false>(r, xf, r.rg_rec, sprim[i], eye, dw, vv, znear, 0, -1, h);
+      }
+      if (key != ZEMPTY) { *z = ZEMPTY; merge_mesh_hit(r, key, h); }
+      const size_t pix = rot == 0 ? ((size_t)lo * H + v) * W + u
+                       : rot == 1 ? ((size_t)lo * W + (W - 1 - u)) * H + v
+                                  : ((size_t)lo * W + u) * H + (H - 1 - v);
+      // ---- shade (the arithmetic of shade_fast with the light loop unrolled over registers)
+      float x = h.t;
+      int k = h.k;
+      if (x < 0 || x > zfar) { x = zfar; k = -1; }
+      if (depth) depth[pix] = (depth_limit > 0 && x > depth_limit) ? 0.f : x;
+      if (!rgb) continue;
+      float col[3];
+      const float idw = rsqrtf(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);
+      if (k < 0) {
+        const float tt = 0.5f * (1.0f + dw[2] * idw);
+#pragma unroll
+        for (int a = 0; a < 3; a++) col[a] = r.nsky >= 2 ? tt * r.sky[a] + (1 - tt) * r.sky[3 + a] : 0.f;
+      } else {
+        const float4* sh4 = reinterpret_cast<const float4*>(r.rg_shade + 8 * k);
+        const float4 s0 = __ldg(sh4), s1 = __ldg(sh4 + 1);
+        const float4* x4 = reinterpret_cast<const float4*>(xf + 12 * k);
+        const float4 t0 = x4[0], t1 = x4[1], t2 = x4[2];
+        float n[3] = {t0.w * h.n[0] + t1.x * h.n[1] + t1.y * h.n[2], t1.z * h.n[0] + t1.w * h.n[1] + t2.x * h.n[2], t2.y * h.n[0] + t2.z * h.n[1] + t2.w * h.n[2]};
+        const float inv = rsqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        const float vw[3] = {-dw[0] * idw, -dw[1] * idw, -dw[2] * idw};
+        const float sgn = (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) ? -inv : inv;   // two-sided lighting
+        n[0] *= sgn; n[1] *= sgn; n[2] *= sgn;
+        const float pos[3] = {eye[0] + x * dw[0], eye[1] + x * dw[1], eye[2] + x * dw[2]};
+        float base[3] = {s0.x, s0.y, s0.z};
+        const float spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
+        if (r.ntex) texture_modulate(r, k, xf + 12 * k, pos, base);
+        float da[3] = {emis, emis, emis}, sa[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int l = 0; l < NSLOT; l++) {
+          float L[3] = {Lv[l][0], Lv[l][1], Lv[l][2]};
+          if (Lv[l][3] > 0.f) {   // positional light
+            L[0] -= pos[0]; L[1] -= pos[1]; L[2] -= pos[2];
+            const float il = rsqrtf(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+            L[0] *= il; L[1] *= il; L[2] *= il;
+          }
+          const float nl = fmaxf(n[0] * L[0] + n[1] * L[1] + n[2] * L[2], 0.f);
+          float hs = 0.f;
+          if (nl > 0) {
+            const float hv[3] = {L[0] + vw[0], L[1] + vw[1], L[2] + vw[2]};
+            const float ih = rsqrtf(hv[0] * hv[0] + hv[1] * hv[1] + hv[2] * hv[2]);
+            hs = __powf(fmaxf((n[0] * hv[0] + n[1] * hv[1] + n[2] * hv[2]) * ih, 0.f), shininess);
+          }
+#pragma unroll
+          for (int a = 0; a < 3; a++) { da[a] += Lc[l][a] + Lc[l][3 + a] * nl; sa[a] = fmaf(Lc[l][6 + a], hs, sa[a]); }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) col[a] = base[a] * da[a] + spec * sa[a];
+      }
+      uint8_t* px = rgb + 3 * pix;
+#pragma unroll
+      for (int a = 0; a < 3; a++) px[bgr ? 2 - a : a] = (uint8_t)(fminf(fmaxf(col[a], 0.f), 1.f) * 255.0f + 0.5f);
     }
-    const size_t pix = rot == 0 ? ((size_t)lo * H + v) * W + u
-                     : rot == 1 ? ((size_t)lo * W + (W - 1 - u)) * H + v
-                                : ((size_t)lo * W + u) * H + (H - 1 - v);
-    shade_fast(r, h.t, h.k, h.n, dw, cam_eye, lvec, lcol, ns, xf, zfar, pix, rgb, depth, depth_limit, bgr);
   }
 }
 
@@ -1441,8 +1546,17 @@ extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fo
         fprintf(stderr, "[raster] %d envs, %d chunks of %d in view; per env: %.0f triangles with a pixel box, %.0f box pixels | large: %.0f tris, %.0f px | near-crossing: %.0f tris, %.0f px | > 4096 px: %.1f tris, %.0f px\n",
                 n, (int)(h[0] / n), r.nchunk, (double)h[1] / n, (double)h[2] / n, (double)h[3] / n, (double)h[4] / n, (double)h[5] / n, (double)h[6] / n, (double)h[7] / n, (double)h[8] / n);
       }
-      raster_resolve_kernel<<<dim3((W + 31) / 32, (H + 31) / 32, n), dim3(32, 8), 0, st>>>(r, e0, off, cam, W, H, B->bufs.xpos, B->bufs.xquat, B->ray_xf,
-                                                                                         B->rs_cam, B->rs_prim, B->zbuf, rgb, depth, depth_limit, post);
+      {
+        const dim3 rg((W + 31) / 32, (H + 31) / 32, n), rb(32, 8);
+        const int nslot = (r.headlight_active ? 1 : 0) + std::min(r.nlight, MAXLIGHT - 1);
+#define SS_RESOLVE(NS) raster_resolve_kernel<NS><<<rg, rb, 0, st>>>(r, e0, off, cam, W, H, B->bufs.xpos, B->bufs.xquat, B->ray_xf, B->rs_cam, B->rs_prim, \
+                                                                   B->zbuf, rgb, depth, depth_limit, post)
+        if (!rgb || nslot < 1 || nslot > 3) SS_RESOLVE(0);
+        else if (nslot == 1) SS_RESOLVE(1);
+        else if (nslot == 2) SS_RESOLVE(2);
+        else SS_RESOLVE(3);
+#undef SS_RESOLVE
+      }
       B->launches += 4;
     }
     CUDA_OK(cudaGetLastError());
