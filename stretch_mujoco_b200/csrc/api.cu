@@ -119,7 +119,9 @@ static int build_layout(DevModel& m, int kernel) {
     o.xmat = take(nb * 9); o.cinert = take(nb * 10);
     o.cacc = take(nb * 10); o.cfrc = take(nb * 6);
     o.crb = o.cacc;                      // composite inertias (10/body) die before the RNE accelerations (6/body) are born
-    o.dpos = take(nb * 3); o.danchor = take(nv * 3);
+    // local offsets of the mass-matrix build (kinematics -> crb_mass_matrix) die before the RNE forces are born: same region
+    if (nb * 3 + nv * 3 <= nb * 6) { o.dpos = o.cfrc; o.danchor = o.cfrc + nb * 3; }
+    else { o.dpos = take(nb * 3); o.danchor = take(nv * 3); }
   } else {
     off = o.pbA;                         // part B stays in global memory: its offsets are only valid against the global block
     o.qacc = take(nv); o.qacc_smooth = take(nv); o.qfrc_con = take(nv);
