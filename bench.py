@@ -450,8 +450,13 @@ def run_ours(args, cfg):
         # 828 algorithmic bytes of an env-step (the whole step's state traffic is attributed to it)
         kernel_ms = float(kms[2])
         achieved = ALGO_BYTES_PER_ENV_STEP * nenv / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture, scaled from the captured
+    # launch (envs_per_launch envs) to this launch (all nenv envs of one profile_step launch); null for the sensor configs
+    traffic = prof.get(args.config, {}).get("dram_bytes_per_launch")
+    if traffic is not None and prof.get("envs_per_launch"):
+        traffic = traffic * nenv / prof["envs_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof.get(args.config, {}).get("dram_bytes_per_launch"), "kernel": kernel, "kernel_ms": kernel_ms,
+                "traffic": traffic, "kernel": kernel, "kernel_ms": kernel_ms,
                 "kernels_ms_per_mj_step": None if kms is None else {"ss_smooth_kernel": float(kms[0]), "ss_narrow_kernel": float(kms[1]),
                                                                     "ss_solve_kernel": float(kms[2]), "note": "serialised, one env set"},
                 "step_frac_of_roofline": algo / (step_ms * 1e-3) / 1e9 / peak,
