@@ -116,6 +116,8 @@ om_model* om_model_load(const void* buf, size_t nbytes) {
       size_t c2 = ss_blob_count(&b, "tex_rgb");
       const unsigned char* tp = ss_blob_u8(&b, "tex_rgb");
       m->tex_rgb = (unsigned char*)malloc(c2 ? c2 : 1); if (c2 && tp) memcpy(m->tex_rgb, tp, c2);
+      const float* uf = ss_blob_f32(&b, "rmesh_uv"); size_t c3 = ss_blob_count(&b, "rmesh_uv");
+      if (uf && c3) { m->rmesh_uv = (float*)malloc(c3 * 4); memcpy(m->rmesh_uv, uf, c3 * 4); }
     }
   }
 #undef D

@@ -51,6 +51,7 @@ struct om_model {
   double* geom_tex;                 /* [ngeom,4] texture index (-1 none), texrepeat x/y, texuniform (NULL: blob without textures) */
   int *tex_adr, *tex_w, *tex_h, ntex;
   unsigned char* tex_rgb;
+  float* rmesh_uv;                  /* [nface,6] UV pairs per triangle (NULL: none) */
   int *light_bodyid, *light_directional;
   double *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;
 };

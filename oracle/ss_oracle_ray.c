@@ -344,8 +344,35 @@ static void shade_pixel(const om_model* m, int g, const double* pos, const doubl
     const double* tx = m->geom_tex + 4 * g;
     double d[3] = {pos[0] - gpos[0], pos[1] - gpos[1], pos[2] - gpos[2]};
     double lx = gmat[0] * d[0] + gmat[3] * d[1] + gmat[6] * d[2], ly = gmat[1] * d[0] + gmat[4] * d[1] + gmat[7] * d[2];
-    double sx = m->geom_size[3 * g], sy = m->geom_size[3 * g + 1], s, t, c[3];
-    if (tx[3] != 0 || sx <= 0 || sy <= 0) { s = lx * tx[1]; t = ly * tx[2]; }
+    double sx = m->geom_size[3 * g], sy = m->geom_size[3 * g + 1], s = 0, t = 0, c[3];
+    if (tx[3] == 2) {
+      /* the mesh's UV set: the triangle that holds the hit point (searched over the whole mesh -- textured meshes are
+         stickers of < 100 triangles), barycentric interpolation of its three UV pairs */
+      int mid = m->geom_dataid[g], nf = m->rmesh_facenum[mid];
+      const float* V = m->rmesh_vert + 3 * m->rmesh_vertadr[mid];
+      const int* F = m->rmesh_face + 3 * m->rmesh_faceadr[mid];
+      const float* UV = m->rmesh_uv ? m->rmesh_uv + 6 * (size_t)m->rmesh_faceadr[mid] : NULL;
+      double lz = gmat[2] * d[0] + gmat[5] * d[1] + gmat[8] * d[2], p[3] = {lx, ly, lz}, bestd = 1e30;
+      for (int f = 0; f < nf && UV; f++) {
+        const float *v0 = V + 3 * F[3 * f], *v1 = V + 3 * F[3 * f + 1], *v2 = V + 3 * F[3 * f + 2];
+        double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+        double w[3] = {p[0] - v0[0], p[1] - v0[1], p[2] - v0[2]}, nn[3];
+        double d00 = v3dot(e1, e1), d01 = v3dot(e1, e2), d11 = v3dot(e2, e2), d20 = v3dot(w, e1), d21 = v3dot(w, e2);
+        double den = d00 * d11 - d01 * d01;
+        if (fabs(den) < 1e-30) continue;
+        double bu = (d11 * d20 - d01 * d21) / den, bv = (d00 * d21 - d01 * d20) / den;
+        if (bu < -1e-6 || bv < -1e-6 || bu + bv > 1 + 1e-6) continue;
+        v3cross(nn, e1, e2);
+        double dist = fabs(v3dot(w, nn)) / sqrt(v3dot(nn, nn));
+        if (dist < bestd) {
+          bestd = dist;
+          const float* uv = UV + 6 * f;
+          s = (uv[0] + bu * (uv[2] - uv[0]) + bv * (uv[4] - uv[0])) * tx[1];
+          t = (uv[1] + bu * (uv[3] - uv[1]) + bv * (uv[5] - uv[1])) * tx[2];
+        }
+      }
+    }
+    else if (tx[3] != 0 || sx <= 0 || sy <= 0) { s = lx * tx[1]; t = ly * tx[2]; }
     else { s = (lx / (2 * sx) + 0.5) * tx[1]; t = (ly / (2 * sy) + 0.5) * tx[2]; }
     tex_sample(m, (int)tx[0], s, t, c);
     for (int k = 0; k < 3; k++) sh[k] *= c[k];

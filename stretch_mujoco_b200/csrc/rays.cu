@@ -152,6 +152,8 @@ int ss_rays_model_init(ss_model* M) {
   const float* V = ss_blob_f32(&b, "rmesh_vert");
   const int32_t* F = ss_blob_i32(&b, "rmesh_face");
   HostBVH H;
+  std::vector<float2> tri_uv;   // 3 per triangle (uv0, uv1 - uv0, uv2 - uv0), leaf order like H.tris
+  const float* UVsrc = ss_blob_f32(&b, "rmesh_uv");
   std::vector<int> bvhadr(vadr.size(), 0), bvhcnt(vadr.size(), 0), tribase(vadr.size(), 0);
   std::vector<float4> mbox(2 * vadr.size(), make_float4(0, 0, 0, 0));
   for (size_t mid = 0; mid < vadr.size(); mid++) {
@@ -181,6 +183,11 @@ int ss_rays_model_init(ss_model* M) {
       H.tris.push_back(make_float4(a[0], a[1], a[2], 0));
       H.tris.push_back(make_float4(c1[0] - a[0], c1[1] - a[1], c1[2] - a[2], 0));
       H.tris.push_back(make_float4(c2[0] - a[0], c2[1] - a[1], c2[2] - a[2], 0));
+      if (UVsrc) {
+        const float* uv = UVsrc + 6 * ((size_t)fadr[mid] + B.order[i]);
+        tri_uv.push_back(make_float2(uv[0], uv[1])); tri_uv.push_back(make_float2(uv[2] - uv[0], uv[3] - uv[1]));
+        tri_uv.push_back(make_float2(uv[4] - uv[0], uv[5] - uv[1]));
+      }
     }
   }
   // per ray-geom record used by the tracing blocks: (type, mesh root ref, root triangle count, body | group << 16),
@@ -228,7 +235,10 @@ int ss_rays_model_init(ss_model* M) {
       }
     }
     r.ntex = (int)tinfo.size();
+    // the material record's (unused) alpha slot tells the shaders whether the geom is textured: no extra load for the rest
+    for (size_t k = 0; k < rg.size(); k++) t_shade[8 * k + 3] = rgtex[k].x >= 0.f ? 1.f : 0.f;
     r.rg_tex = upload(M, rgtex); r.tex_info = upload(M, tinfo); r.tex_rgb = upload(M, texels);
+    r.tri_uv = (UVsrc && tri_uv.size() == H.tris.size()) ? upload(M, tri_uv) : nullptr;
   }
   // raster work chunks of the camera-visible mesh geoms (groups 0..2)
   {
@@ -331,7 +341,7 @@ __global__ void ray_prepare_kernel(RayModel r, int env_begin, int nenv, const fl
   q2m(o + 3, q);
 }
 
-struct Hit { float t; int k; float n[3]; };  // k = index into the ray-geom list; n = local-frame normal (unnormalised)
+struct Hit { float t; int k; float n[3]; int tri; };  // k = index into the ray-geom list; n = local-frame normal (unnormalised); tri = triangle (meshes)
 
 // slab test of the ray (o, 1/d) against the box [lo, hi] on [0, tmax]; entry distance in *tnear
 __device__ __forceinline__ bool slab(float lx, float ly, float lz, float hx, float hy, float hz, const float* o, const float* inv,
@@ -373,6 +383,7 @@ __device__ float trace_mesh(const RayModel& r, int ref, int cnt, const float* o,
         if (x >= tmin && (best < 0 || x < best)) {
           best = x; found = true;
           nrm[0] = e1.y * e2.z - e1.z * e2.y; nrm[1] = e1.z * e2.x - e1.x * e2.z; nrm[2] = e1.x * e2.y - e1.y * e2.x;
+          nrm[3] = __int_as_float(i);
         }
       }
     } else {
@@ -504,15 +515,16 @@ __device__ __forceinline__ void trace_one(const RayModel& r, const float* xf, co
   const float* R = T + 3;
   float o[3] = {R[0] * dif[0] + R[3] * dif[1] + R[6] * dif[2], R[1] * dif[0] + R[4] * dif[1] + R[7] * dif[2], R[2] * dif[0] + R[5] * dif[1] + R[8] * dif[2]};
   float d[3] = {R[0] * vec[0] + R[3] * vec[1] + R[6] * vec[2], R[1] * vec[0] + R[4] * vec[1] + R[7] * vec[2], R[2] * vec[0] + R[5] * vec[1] + R[8] * vec[2]};
-  float n[3];
+  float n[4];
+  n[3] = __int_as_float(-1);
   float x = trace_geom(r, rec, o, d, tmin, h.t, n);
-  if (x >= 0 && (h.t < 0 || x < h.t)) { h.t = x; h.k = k; h.n[0] = n[0]; h.n[1] = n[1]; h.n[2] = n[2]; }
+  if (x >= 0 && (h.t < 0 || x < h.t)) { h.t = x; h.k = k; h.n[0] = n[0]; h.n[1] = n[1]; h.n[2] = n[2]; h.tri = __float_as_int(n[3]); }
 }
 // nearest hit over all ray-visible geoms of the env (lidar / generic rays)
 template <bool FILTER>
 __device__ Hit trace_scene(const RayModel& r, const float* xf, const float4* recs, int n, const float* pnt, const float* vec, float tmin,
                            int groupmask, int bodyexclude) {
-  Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+  Hit h; h.t = -1.f; h.k = -1; h.tri = -1; h.n[0] = h.n[1] = h.n[2] = 0;
   float vv = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
   for (int k = 0; k < n; k++) trace_one<FILTER>(r, xf, recs, k, pnt, vec, vv, tmin, groupmask, bodyexclude, h);
   return h;
@@ -648,7 +660,7 @@ __global__ void __launch_bounds__(32 * LIDAR_WARPS) lidar_kernel(RayModel r, int
     }
     __syncwarp();
     if (live) {
-      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      Hit h; h.t = -1.f; h.k = -1; h.tri = -1; h.n[0] = h.n[1] = h.n[2] = 0;
       const float vv = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
       for (int i = 0; i < nl; i++) trace_one<true>(r, sxf, srec, wlist[i], p, dir, vv, 0.f, 0, b, h);
       float dist = h.t;
@@ -685,7 +697,7 @@ __global__ void rays_kernel(RayModel r, int nenv, int nray, const float* __restr
 #define MAXLIGHT 8
 // 2-D texture of ray-geom k at the world point pos (planar x-y projection of the geom frame, GL_REPEAT, bilinear, texel
 // centres at (i + 0.5) / w, image row 0 on top); multiplies the material colour
-__device__ __forceinline__ void texture_modulate(const RayModel& r, int k, const float* T, const float* pos, float* base) {
+__device__ __forceinline__ void texture_modulate(const RayModel& r, int k, int tri, const float* T, const float* pos, float* base) {
   const float4 tx = __ldg(r.rg_tex + k);
   if (tx.x < 0.f) return;
   const float* R = T + 3;
@@ -693,7 +705,20 @@ __device__ __forceinline__ void texture_modulate(const RayModel& r, int k, const
   const float lx = R[0] * d[0] + R[3] * d[1] + R[6] * d[2], ly = R[1] * d[0] + R[4] * d[1] + R[7] * d[2];
   const float4 sz = __ldg(r.rg_rec + 4 * k + 1);   // (rbound, size.xyz)
   float s, t;
-  if (tx.w != 0.f || sz.y <= 0.f || sz.z <= 0.f) { s = lx * tx.y; t = ly * tx.z; }
+  if (tx.w == 2.f) {
+    // the mesh's UV set: barycentric coordinates of the hit point in the winning triangle
+    if (tri < 0 || !r.tri_uv) return;
+    const float lz = R[2] * d[0] + R[5] * d[1] + R[8] * d[2];
+    const float4 v0 = __ldg(r.tri + 3 * (size_t)tri), e1 = __ldg(r.tri + 3 * (size_t)tri + 1), e2 = __ldg(r.tri + 3 * (size_t)tri + 2);
+    const float w[3] = {lx - v0.x, ly - v0.y, lz - v0.z};
+    const float d00 = e1.x * e1.x + e1.y * e1.y + e1.z * e1.z, d01 = e1.x * e2.x + e1.y * e2.y + e1.z * e2.z, d11 = e2.x * e2.x + e2.y * e2.y + e2.z * e2.z;
+    const float d20 = w[0] * e1.x + w[1] * e1.y + w[2] * e1.z, d21 = w[0] * e2.x + w[1] * e2.y + w[2] * e2.z;
+    const float iden = 1.0f / (d00 * d11 - d01 * d01);
+    const float bu = (d11 * d20 - d01 * d21) * iden, bv = (d00 * d21 - d01 * d20) * iden;
+    const float2 uv0 = __ldg(r.tri_uv + 3 * (size_t)tri), du1 = __ldg(r.tri_uv + 3 * (size_t)tri + 1), du2 = __ldg(r.tri_uv + 3 * (size_t)tri + 2);
+    s = (uv0.x + bu * du1.x + bv * du2.x) * tx.y; t = (uv0.y + bu * du1.y + bv * du2.y) * tx.z;
+  }
+  else if (tx.w != 0.f || sz.y <= 0.f || sz.z <= 0.f) { s = lx * tx.y; t = ly * tx.z; }
   else { s = (lx / (2.f * sz.y) + 0.5f) * tx.y; t = (ly / (2.f * sz.z) + 0.5f) * tx.z; }
   const int4 ti = __ldg(r.tex_info + (int)tx.x);
   const int w = ti.y, h = ti.z;
@@ -742,7 +767,7 @@ __device__ __forceinline__ void shade_and_store(const RayModel& r, Hit h, const 
       vw[0] *= inv; vw[1] *= inv; vw[2] *= inv;
       if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
       float base[3] = {sh[0], sh[1], sh[2]};
-      if (r.ntex) texture_modulate(r, h.k, xf + 12 * h.k, pos, base);
+      if (sh[3] > 0.f) texture_modulate(r, h.k, h.tri, xf + 12 * h.k, pos, base);
       for (int a = 0; a < 3; a++) col[a] = base[a] * sh[6];
       float shininess = fmaxf(sh[5] * 128.0f, 1.0f);
       int nl_ = min(r.nlight, MAXLIGHT - 1);
@@ -896,7 +921,7 @@ __global__ void __launch_bounds__(TILE * TILE) render_kernel(RayModel r, int env
   float dl[3] = {(u + 0.5f - 0.5f * W) / f, -(v + 0.5f - 0.5f * H) / f, -1.0f};
   float dw[3] = {cam_R[0] * dl[0] + cam_R[1] * dl[1] + cam_R[2] * dl[2], cam_R[3] * dl[0] + cam_R[4] * dl[1] + cam_R[5] * dl[2],
                  cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
-  Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+  Hit h; h.t = -1.f; h.k = -1; h.tri = -1; h.n[0] = h.n[1] = h.n[2] = 0;
   if (inb) {
     // (a second, per-warp culling level against 16 x 2 pixel strips was measured slower: 21.0 vs 19.7 ms)
     const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
@@ -1174,7 +1199,7 @@ __global__ void __launch_bounds__(256) raster_large_kernel(RayModel r, int W, in
 
 // Pixel epilogue of the raster path: the arithmetic of shade_and_store with the per-frame constants hoisted (vector loads of
 // the material and the geom rotation, light directions normalised once per CTA: lvec[.][3] < 0 marks a unit direction).
-__device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, const float* hn, const float* dw, const float* cam_eye,
+__device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, int tri, const float* hn, const float* dw, const float* cam_eye,
                                            const float (*lvec)[4], const float (*lcol)[9], int nslot, const float* xf, float zfar, size_t pix,
                                            uint8_t* __restrict__ rgb, float* __restrict__ depth, float depth_limit, int bgr) {
   if (x < 0 || x > zfar) { x = zfar; k = -1; }
@@ -1199,7 +1224,7 @@ __device__ __forceinline__ void shade_fast(const RayModel& r, float x, int k, co
     if (n[0] * vw[0] + n[1] * vw[1] + n[2] * vw[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
     float base[3] = {s0.x, s0.y, s0.z};
     const float spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
-    if (r.ntex) texture_modulate(r, k, xf + 12 * k, pos, base);
+    if (s0.w > 0.f) texture_modulate(r, k, tri, xf + 12 * k, pos, base);
     // col = base * (emission + sum_l (ambient_l + diffuse_l nl_l)) + specular * sum_l specular_l hs_l
     float da[3] = {emis, emis, emis}, sa[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < nslot; l++) {
@@ -1246,7 +1271,7 @@ __device__ __forceinline__ void plane_hit(const SPlane& P, const float* dw, floa
     const float py = P.oy + x * (P.ay[0] * dw[0] + P.ay[1] * dw[1] + P.ay[2] * dw[2]);
     if ((P.s0 > 0 && fabsf(px) > P.s0) || (P.s1 > 0 && fabsf(py) > P.s1)) return;
   }
-  h.t = x; h.k = P.k; h.n[0] = 0.f; h.n[1] = 0.f; h.n[2] = 1.f;
+  h.t = x; h.k = P.k; h.tri = -1; h.n[0] = 0.f; h.n[1] = 0.f; h.n[2] = 1.f;
 }
 // the depth/id buffer's winner replaces the primitive hit when it is nearer
 __device__ __forceinline__ void merge_mesh_hit(const RayModel& r, unsigned long long key, Hit& h) {
@@ -1255,7 +1280,7 @@ __device__ __forceinline__ void merge_mesh_hit(const RayModel& r, unsigned long 
     const unsigned id = (unsigned)key;
     const size_t ti = id & 0x3fffffu;
     const float4 e1 = __ldg(r.tri + 3 * ti + 1), e2 = __ldg(r.tri + 3 * ti + 2);
-    h.t = x; h.k = (int)(id >> 22);
+    h.t = x; h.k = (int)(id >> 22); h.tri = (int)ti;
     h.n[0] = e1.y * e2.z - e1.z * e2.y; h.n[1] = e1.z * e2.x - e1.x * e2.z; h.n[2] = e1.x * e2.y - e1.y * e2.x;
   }
 }
@@ -1333,7 +1358,7 @@ __global__ void __launch_bounds__(256, RESOLVE_CTAS) raster_resolve_kernel(RayMo
                      cam_R[6] * dl[0] + cam_R[7] * dl[1] + cam_R[8] * dl[2]};
       unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
       const unsigned long long key = *z;
-      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      Hit h; h.t = -1.f; h.k = -1; h.tri = -1; h.n[0] = h.n[1] = h.n[2] = 0;
       for (int i = 0; i < npl; i++) plane_hit(planes[i], dw, znear, h);
       if (np) {
         const float vv = dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2];
@@ -1343,7 +1368,7 @@ __global__ void __launch_bounds__(256, RESOLVE_CTAS) raster_resolve_kernel(RayMo
       const size_t pix = rot == 0 ? ((size_t)lo * H + v) * W + u
                        : rot == 1 ? ((size_t)lo * W + (W - 1 - u)) * H + v
                                   : ((size_t)lo * W + u) * H + (H - 1 - v);
-      shade_fast(r, h.t, h.k, h.n, dw, cam_eye, lvec, lcol, ns, xf, zfar, pix, rgb, depth, depth_limit, bgr);
+      shade_fast(r, h.t, h.k, h.tri, h.n, dw, cam_eye, lvec, lcol, ns, xf, zfar, pix, rgb, depth, depth_limit, bgr);
     }
   } else {
     // NSLOT light slots known at launch: camera, first plane and lights live in registers for the four rows of the tile
@@ -1371,12 +1396,12 @@ __global__ void __launch_bounds__(256, RESOLVE_CTAS) raster_resolve_kernel(RayMo
       const float dw[3] = {cR[0] * dx + cR[1] * dy - cR[2], cR[3] * dx + cR[4] * dy - cR[5], cR[6] * dx + cR[7] * dy - cR[8]};
       unsigned long long* z = zbuf + ((size_t)le * H + v) * W + u;
       const unsigned long long key = *z;
-      Hit h; h.t = -1.f; h.k = -1; h.n[0] = h.n[1] = h.n[2] = 0;
+      Hit h; h.t = -1.f; h.k = -1; h.tri = -1; h.n[0] = h.n[1] = h.n[2] = 0;
       if (p0) {
         const float d2 = pn[0] * dw[0] + pn[1] * dw[1] + pn[2] * dw[2];
         if (d2 <= -1e-15f) {
           const float x = -pc0 / d2;
-          if (x >= znear) { h.t = x; h.k = pk; h.n[2] = 1.f; }
+          if (x >= znear) { h.t = x; h.k = pk; h.tri = -1; h.n[2] = 1.f; }
         }
       }
       for (int i = p0 ? 1 : 0; i < npl; i++) plane_hit(planes[i], dw, znear, h);
@@ -1413,7 +1438,7 @@ __global__ void __launch_bounds__(256, RESOLVE_CTAS) raster_resolve_kernel(RayMo
         const float pos[3] = {eye[0] + x * dw[0], eye[1] + x * dw[1], eye[2] + x * dw[2]};
         float base[3] = {s0.x, s0.y, s0.z};
         const float spec = s1.x, shininess = fmaxf(s1.y * 128.0f, 1.0f), emis = s1.z;
-        if (r.ntex) texture_modulate(r, k, xf + 12 * k, pos, base);
+        if (s0.w > 0.f) texture_modulate(r, k, h.tri, xf + 12 * k, pos, base);
         float da[3] = {emis, emis, emis}, sa[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int l = 0; l < NSLOT; l++) {

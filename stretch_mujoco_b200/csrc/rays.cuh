@@ -30,6 +30,7 @@ struct RayModel {
   const float4* rg_tex;
   const int4* tex_info;
   const unsigned char* tex_rgb;
+  const float2* tri_uv;     // 3 per triangle of `tri` (uv0, uv1 - uv0, uv2 - uv0) or nullptr: UV sets of textured meshes
   int ntex;
   const int *light_bodyid, *light_directional;
   const float *light_pos, *light_dir, *light_ambient, *light_diffuse, *light_specular;

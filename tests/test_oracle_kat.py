@@ -234,11 +234,14 @@ def test_wood_table_texture():
     from stretch_mujoco_b200 import blob
     raw = blob.read_bytes(os.path.join(os.path.dirname(__file__), "golden", "stretch_default_scene_render.ssm.z"))
     A, names = blob.unpack(raw)
-    assert int((A["geom_tex"][:, 0] >= 0).sum()) == 1 and A["tex_w"][0] == 512 and A["tex_h"][0] == 512
+    box = (A["geom_tex"][:, 0] >= 0) & (A["geom_tex"][:, 3] != 2)           # the table; the robot's stickers use their UV sets (mode 2)
+    assert int(box.sum()) == 1
+    t = int(A["geom_tex"][box, 0][0])
+    assert A["tex_w"][t] == 512 and A["tex_h"][t] == 512
     om = OracleModel(raw); om.set_options(enable_lidar=False)
     o, cam = _table_view(A, names, om)
     rgb, depth = om.render(o["xpos"], o["xquat"], cam, 96, 72, 42.0)
-    A2 = dict(A); A2["geom_tex"] = A["geom_tex"].copy(); A2["geom_tex"][:, 0] = -1
+    A2 = dict(A); A2["geom_tex"] = A["geom_tex"].copy(); A2["geom_tex"][box, 0] = -1
     om2 = OracleModel(blob.pack(A2, names)); om2.set_options(enable_lidar=False)
     rgb2, depth2 = om2.render(o["xpos"], o["xquat"], cam, 96, 72, 42.0)
     assert np.array_equal(depth, depth2)
@@ -250,3 +253,27 @@ def test_wood_table_texture():
     assert 1.4 < mean[0] / mean[2] < 1.8 and 1.2 < mean[1] / mean[2] < 1.45, mean
     assert tex.std(0).min() > 5.0                                        # wood grain, not a flat colour
     assert tex.std(0).min() > 1.5 * rgb2[0][changed].std(0).max()        # ... against the smooth shading of the untextured table
+
+
+def test_aruco_stickers_are_textured():
+    """The robot's ArUco / label stickers are small meshes with UV sets behind `<material texture=...>` (models/stretch.xml:82-126,
+    405-429): the wrist camera looks at the two finger markers.  Against the same model with textures off, the pixels that change
+    are the stickers, and they show the marker's black cells and white border instead of a flat colour."""
+    import os
+    from oracle.oracle import OracleModel
+    from stretch_mujoco_b200 import blob
+    raw = blob.read_bytes(os.path.join(os.path.dirname(__file__), "golden", "stretch_empty_floor_render.ssm.z"))
+    A, names = blob.unpack(raw)
+    assert int((A["geom_tex"][:, 3] == 2).sum()) >= 8 and A["rmesh_uv"].shape == (len(A["rmesh_face"]), 6)
+    om = OracleModel(raw); om.set_options(enable_lidar=False)
+    q = A["qpos0"][None].copy()
+    o = om.step(q, np.zeros((1, om.nv)), A["key_ctrl"][0][None].copy(), np.zeros((1, om.nv)), nsteps=800, want=("xpos", "xquat"))
+    A2 = dict(A); A2["geom_tex"] = A["geom_tex"].copy(); A2["geom_tex"][:, 0] = -1
+    om2 = OracleModel(blob.pack(A2, names)); om2.set_options(enable_lidar=False)
+    cam = names[compiler.OBJ_CAMERA].index("d405_rgb")
+    rgb, _ = om.render(o["xpos"], o["xquat"], cam, 120, 68, 58.0)
+    rgb2, _ = om2.render(o["xpos"], o["xquat"], cam, 120, 68, 58.0)
+    changed = np.abs(rgb.astype(int) - rgb2.astype(int)).max(-1)[0] > 8
+    px = rgb[0][changed]
+    assert 30 <= changed.sum() <= 400                                   # two finger markers, a few dozen pixels at this size
+    assert (px.max(-1) < 60).sum() >= 20 and (px.min(-1) > 150).sum() >= 4   # black cells and white border
