@@ -493,6 +493,7 @@ extern "C" int ss_batch_create(const ss_model* M, int nenv, int maxcon, int maxe
   if (const char* e = getenv("SS_RENDER")) B->render_mode = strcmp(e, "raycast") == 0 ? 0 : 1;   // A/B knob: the ray-cast camera path
   if (const char* e = getenv("SS_RASTER_NSUB")) B->raster_nsub = std::max(1, atoi(e));
   B->raster_stats = getenv("SS_RASTER_STATS") != nullptr;
+  if (const char* e = getenv("SS_RASTER_QCAP")) B->raster_qcap = std::max(1, atoi(e));
   B->nosort = getenv("SS_NOSORT") != nullptr;
   // schedule key: bucket = min(255, cost_scale * cost), cost = cost_w x Newton iterations + narrowphase queries
   // (47.3 ms per 50 steps for 16 / x1 against 47.9 ms for 8 / x4)

@@ -60,6 +60,7 @@ struct ss_batch {
   int rs_qcap = 0;
   int rs_nsub = 0;
   int raster_nsub = 0;                       // SS_RASTER_NSUB: envs per raster sub-chunk (0 = automatic)
+  int raster_qcap = 0;                       // SS_RASTER_QCAP: queue capacity override (test of the overflow path)
   bool raster_stats = false;                 // SS_RASTER_STATS: print work counters per sub-chunk (diagnostic)
 };
 

@@ -1551,7 +1551,7 @@ extern "C" int ss_batch_render_post(ss_batch* B, int cam, int W, int H, float fo
       CUDA_OK(cudaMalloc((void**)&B->rs_prim, (size_t)nsub * (MAXPRIM + 1) * sizeof(int)));
       CUDA_OK(cudaMalloc((void**)&B->rs_cvis, (size_t)nsub * r.nchunk));
       if (B->rs_queue) { cudaFree(B->rs_queue); cudaFree(B->rs_qcount); }
-      B->rs_qcap = nsub * 4096;
+      B->rs_qcap = B->raster_qcap > 0 ? B->raster_qcap : nsub * 4096;   // a full queue sends the box back to its owner warp (raster_tri_kernel)
       CUDA_OK(cudaMalloc((void**)&B->rs_queue, (size_t)B->rs_qcap * sizeof(RItem)));
       CUDA_OK(cudaMalloc((void**)&B->rs_qcount, sizeof(int)));
       B->rs_nsub = nsub;

@@ -434,3 +434,28 @@ def test_wood_table_texture_on_the_device():
         assert (np.abs(c.astype(int) - rrgb.astype(int)).max(axis=-1) <= 2).mean() > 0.99, mode
         table = (rdepth[0] > 0.5) & (rdepth[0] < 2.0) & (rrgb[0, :, :, 0].astype(int) > rrgb[0, :, :, 2].astype(int) + 30)   # wood: red well above blue
         assert table.mean() > 0.25 and c[0][table].std(0).min() > 5.0, mode
+
+
+def test_raster_queue_overflow_falls_back_to_the_owner_warp(render_scene):
+    """Pixel boxes that do not fit the work queue of raster_large_kernel are walked by the warp that owns the triangle:
+    with a 16-item queue (SS_RASTER_QCAP) and 3-env sub-chunks the images are identical to the default configuration."""
+    from stretch_mujoco_b200 import engine
+    dm, B0 = render_scene["dm"], render_scene["B"]
+    cam = dm.name2id(engine.OBJ_CAMERA, "d405_rgb")
+    W, H = 480, 270
+    outs = []
+    for knobs in ({}, {"SS_RASTER_QCAP": "16", "SS_RASTER_NSUB": "1"}):
+        os.environ.update(knobs)
+        try:
+            B = engine.Batch(dm, 2)
+        finally:
+            for k in knobs:
+                os.environ.pop(k, None)
+        for dst, src in ((B.qpos, B0.qpos), (B.qvel, B0.qvel), (B.ctrl, B0.ctrl)):
+            dst.copy_(src)
+        B.forward()
+        rgb = torch.zeros(2, H, W, 3, dtype=torch.uint8, device="cuda"); depth = torch.zeros(2, H, W, device="cuda")
+        B.render(cam, W, H, 58.0, rgb, depth, 1.0); torch.cuda.synchronize()
+        outs.append((rgb.clone(), depth.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert float((outs[0][1] > 0).float().mean()) > 0.05
