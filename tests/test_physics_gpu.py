@@ -287,3 +287,28 @@ def test_scheduling_does_not_leak_into_results(gpu, arrays_E, monkeypatch):
         assert torch.equal(B1.qpos, B2.qpos) and torch.equal(B1.qvel, B2.qvel) and torch.equal(B1.qacc_warmstart, B2.qacc_warmstart)
         assert torch.equal(B1.xpos, B2.xpos) and torch.equal(B1.contact_geom, B2.contact_geom) and torch.equal(B1.time, B2.time)
     assert B1.launches > B2.launches
+
+
+def test_batch_size_invariance_at_the_bench_size(gpu, arrays_E):
+    """Envs are independent units: env i of BASELINE config 2 (4096 envs, bench.py's ctrl stream from qpos0, two control
+    periods) is bit-identical to the same env simulated in a batch of 1, 7, 33 or 1187 envs -- whatever the CTA shapes,
+    env sets and cost-sorted schedule of the two batches (a size-independent property checked at the full size)."""
+    import bench
+    from stretch_mujoco_b200 import engine
+    A, _ = arrays_E
+    dev = torch.device("cuda")
+    lo = torch.tensor(A["actuator_ctrlrange"][:, 0], dtype=torch.float64, device=dev)
+    hi = torch.tensor(A["actuator_ctrlrange"][:, 1], dtype=torch.float64, device=dev)
+
+    def rollout(env0, n):
+        B = engine.Batch(gpu, n)
+        for p in range(2):
+            B.ctrl.copy_(bench.ctrl_torch(0, env0, n, p, lo, hi, dev)); B.step(50)
+        torch.cuda.synchronize()
+        return B.qpos.clone(), B.qvel.clone(), B.qacc_warmstart.clone(), B.contact_geom.clone()
+
+    big = rollout(0, 4096)
+    for env0, n in ((0, 1), (5, 7), (100, 33), (2900, 1187)):
+        small = rollout(env0, n)
+        for a, b in zip(big, small):
+            assert torch.equal(a[env0:env0 + n], b), (env0, n)
